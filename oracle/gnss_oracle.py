@@ -1,0 +1,284 @@
+"""CPU oracle for the acquisition and tracking hot paths  --  TEST INFRASTRUCTURE ONLY.
+
+A float64 numpy restatement of what the reference computes (it is *not* shipped and
+the product never imports it: only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may).  Every function
+cites the reference lines it follows (paths relative to the reference repo).
+
+Pinning: the reference has no tests or golden vectors of its own,
+so this restatement is pinned against the reference itself, run in the build
+container through the mechanical Python-3 shim (``oracle/make_ref_shim.py``):
+
+* ``tests/golden/*.npz`` -- outputs of the shimmed reference on seeded synthetic
+  recordings, produced by ``tests/golden/make_golden.py`` (committed with the data);
+* ``tests/test_oracle_vs_reference.py`` -- live diff when ``/root/reference`` exists.
+
+Arithmetic that the reference delegates to numpy (pocketfft ``np.fft``, ufuncs) is
+delegated to the same numpy calls here (numpy 2.3.5 in this image; the reference
+pins no version, README.md:7-10).
+
+The ``coherent_ms`` / ``noncoh_blocks`` / ``doppler_step`` arguments of
+:func:`acquire` are extensions with *no* reference behaviour (BASELINE.json configs 3
+and 5); at their defaults (1, 2, 500.0) the function reduces to the reference.
+"""
+import numpy as np
+
+TWO_PI = 2 * np.pi
+
+_G2S = [5, 6, 7, 8, 17, 18, 139, 140, 141, 251, 252, 254, 255, 256, 257, 258, 469, 470, 471,
+        472, 473, 474, 509, 512, 513, 514, 515, 516, 859, 860, 861, 862]
+
+
+# --------------------------------------------------------------------------- helpers
+def samples_per_code(s):
+    """initialize.py:183-185."""
+    return int(np.round(s.samplingFreq / (s.codeFreqBasis / s.codeLength)))
+
+
+def ca_code(prn0):
+    """initialize.py:234-302 -- +-1 register arithmetic as the reference does it."""
+    assert 0 <= prn0 < 32
+
+    def run(tap_idx):
+        reg = -np.ones(10)
+        seq = np.zeros(1023)
+        for i in range(1023):
+            seq[i] = reg[9]
+            fb = np.prod(reg[tap_idx])
+            reg[1:] = reg[:-1].copy()
+            reg[0] = fb
+        return seq
+
+    g1 = run([2, 9])                      # :272
+    g2 = run([1, 2, 5, 7, 8, 9])          # :290
+    sh = _G2S[prn0]
+    g2 = np.concatenate((g2[1023 - sh:], g2[:1023 - sh]))   # :298
+    return -g1 * g2                       # :301
+
+
+_CODE_CACHE = {}
+
+
+def ca_code_cached(prn0):
+    if prn0 not in _CODE_CACHE:
+        _CODE_CACHE[prn0] = ca_code(prn0)
+    return _CODE_CACHE[prn0]
+
+
+def ca_table(s):
+    """initialize.py:188-231."""
+    n = samples_per_code(s)
+    ts = 1.0 / s.samplingFreq
+    tc = 1.0 / s.codeFreqBasis
+    idx = np.ceil(ts * np.arange(1, n + 1) / tc) - 1        # :223
+    idx = idx.astype(np.int64)
+    idx[-1] = 1022                                          # :226
+    return np.array([ca_code_cached(p)[idx] for p in range(32)])
+
+
+def loop_coef(lbw, zeta, k):
+    """initialize.py:306-328."""
+    wn = lbw * 8.0 * zeta / (4.0 * zeta ** 2 + 1)
+    return k / (wn * wn), 2.0 * zeta / wn
+
+
+# --------------------------------------------------------------------------- acquisition
+def _exclusion_range(code_phase, chip_samples, n):
+    """acquisition.py:147-159 -- candidate indices for the second peak (may contain
+    negative values, which index from the end exactly as numpy does there)."""
+    lo = code_phase - chip_samples
+    hi = code_phase + chip_samples
+    if lo <= 0:
+        return np.arange(hi, n + lo + 1)
+    if hi >= n - 1:
+        return np.arange(hi - n, lo)
+    return np.concatenate((np.arange(0, lo + 1), np.arange(hi, n)))
+
+
+def acquire(long_signal, s, coherent_ms=1, noncoh_blocks=2, doppler_step=500.0,
+            return_debug=False, clamp_window=False):
+    """acquisition.py:49-204.  Returns dict(carrFreq, codePhase, peakMetric) (float64[32]).
+
+    ``clamp_window=True`` drops the out-of-range index the reference generates when
+    codePhase == samplesPerCodeChip (its IndexError) --
+    that is the behaviour the CUDA path implements for that one case.
+    """
+    n1 = samples_per_code(s)
+    n = n1 * coherent_ms
+    x = np.asarray(long_signal)
+    blocks = [x[b * n:(b + 1) * n] for b in range(noncoh_blocks)]          # :55-57
+    x0 = x - x.mean()                                                      # :59
+    ts = 1.0 / s.samplingFreq
+    phase_pts = np.arange(n) * 2 * np.pi * ts                              # :65
+    if doppler_step == 500.0:
+        nbins = int(np.round(s.acqSearchBand * 2) + 1)                     # :68
+    else:
+        nbins = int(np.round(s.acqSearchBand * 1000.0 / doppler_step) + 1)
+    table = ca_table(s)                                                    # :71
+    if coherent_ms > 1:
+        table = np.tile(table, (1, coherent_ms))
+    nprn = len(s.acqSatelliteList)                                         # :92 (length only)
+    carr = np.zeros(32)
+    cph = np.zeros(32)
+    metric = np.zeros(32)
+    dbg = {}
+    freqs = np.array([s.IF - s.acqSearchBand / 2 * 1000 + doppler_step * k
+                      for k in range(nbins)])                              # :99-101
+    # Carrier wipe-off does not depend on the PRN; do it once per (bin, block).
+    spec = np.empty((noncoh_blocks, nbins, n), dtype=np.complex128)
+    for k in range(nbins):
+        sin_c = np.sin(freqs[k] * phase_pts)                               # :103
+        cos_c = np.cos(freqs[k] * phase_pts)                               # :105
+        for b in range(noncoh_blocks):
+            spec[b, k] = np.fft.fft(sin_c * blocks[b] + 1j * (cos_c * blocks[b]))  # :107-117
+    for prn in range(nprn):
+        code_f = np.fft.fft(table[prn]).conj()                             # :95
+        results = np.zeros((nbins, n))
+        for k in range(nbins):
+            best = None
+            for b in range(noncoh_blocks):
+                r = abs(np.fft.ifft(spec[b, k] * code_f)) ** 2             # :120-126
+                # :129-133 keep block 1 only if strictly larger, later blocks win ties
+                if best is None or not (best.max() > r.max()):
+                    best = r
+            results[k] = best
+        fbin = results.max(1).argmax()                                     # :140
+        peak = results.max(0).max()                                        # :142
+        cp = int(results.max(0).argmax())                                  # :143
+        chip = int(round(s.samplingFreq / s.codeFreqBasis))                # :145
+        rng = _exclusion_range(cp, chip, n)
+        if clamp_window:
+            rng = rng[rng < n]
+        second = results[fbin, rng].max()                                  # :162
+        metric[prn] = peak / second                                        # :164
+        if return_debug:
+            dbg[prn] = dict(bin=int(fbin), codePhase=cp, peak=peak, second=second)
+        if peak / second > s.acqThreshold:                                 # :166
+            code = ca_code_cached(prn)
+            idx = np.floor(ts * np.arange(1, 10 * n1 + 1) / (1.0 / s.codeFreqBasis))   # :172
+            long_code = code[(idx % 1023).astype(np.int64)]                # :174
+            xc = x0[cp:cp + 10 * n1] * long_code                           # :177
+            nfft = int(8 * 2 ** (np.ceil(np.log2(len(xc)))))               # :179
+            mag = np.abs(np.fft.fft(xc, nfft))                             # :182
+            uniq = int(np.ceil((nfft + 1) / 2.0))                          # :184
+            imax = mag[4:uniq - 5].argmax()                                # :187 (slice-relative!)
+            bins = np.arange(uniq) * s.samplingFreq / nfft                 # :189
+            carr[prn] = bins[imax]                                         # :191
+            cph[prn] = cp                                                  # :193
+            if return_debug:
+                dbg[prn]["fineIndex"] = int(imax)
+    out = dict(carrFreq=carr, codePhase=cph, peakMetric=metric)
+    if return_debug:
+        out["debug"] = dbg
+    return out
+
+
+def pre_run(acq, s):
+    """acquisition.py:259-306 -> dict(PRN int64[C], acquiredFreq, codePhase, status list)."""
+    c = s.numberOfChannels
+    prn = np.zeros(c, dtype=np.int64)
+    freq = np.zeros(c)
+    cph = np.zeros(c)
+    status = ['-'] * c
+    order = sorted(enumerate(acq["peakMetric"]), key=lambda t: t[-1], reverse=True)   # :288
+    for i in range(min(c, int(np.sum(acq["carrFreq"] > 0)))):             # :294
+        j = order[i][0]
+        prn[i] = j + 1
+        freq[i] = acq["carrFreq"][j]
+        cph[i] = acq["codePhase"][j]
+        status[i] = 'T'
+    return dict(PRN=prn, acquiredFreq=freq, codePhase=cph, status=status)
+
+
+# --------------------------------------------------------------------------- tracking
+TRACK_FIELDS = ("absoluteSample", "codeFreq", "carrFreq", "I_P", "I_E", "I_L", "Q_E", "Q_P",
+                "Q_L", "dllDiscr", "dllDiscrFilt", "pllDiscr", "pllDiscrFilt")
+
+
+def track_channel(data, prn, acquired_freq, code_phase, s, ms=None):
+    """tracking.py:99-283 for one channel.  ``data`` is the whole int8 recording (the
+    reference reads the same bytes through fid.seek/np.fromfile).  Returns
+    (dict of 13 float64[ms] series, ms_done); ms_done < ms means the short-read exit
+    at tracking.py:159-163 fired."""
+    ms = int(s.msToProcess) if ms is None else int(ms)
+    fs = s.samplingFreq
+    spc = s.dllCorrelatorSpacing
+    t1c, t2c = loop_coef(s.dllNoiseBandwidth, s.dllDampingRatio, 1.0)      # :45
+    t1p, t2p = loop_coef(s.pllNoiseBandwidth, s.pllDampingRatio, 0.25)     # :52
+    pdi = 0.001
+    out = {k: (np.zeros(ms) if k in ("absoluteSample", "I_P", "I_E", "I_L", "Q_E", "Q_P", "Q_L")
+               else np.inf * np.ones(ms)) for k in TRACK_FIELDS}           # :65-94
+    pos = int(s.skipNumberOfBytes + code_phase)                            # :107
+    c = ca_code_cached(int(prn) - 1)
+    code = np.concatenate(([c[-1]], c, [c[0]]))                            # :111
+    code_freq = s.codeFreqBasis
+    rem_code = 0.0
+    carr_freq = acquired_freq
+    carr_basis = acquired_freq
+    rem_carr = 0.0
+    old_code_nco = old_code_err = old_carr_nco = old_carr_err = 0.0
+    done = 0
+    for k in range(ms):
+        step = code_freq / fs                                              # :148
+        blk = int(np.ceil((s.codeLength - rem_code) / step))               # :150
+        raw = data[pos:pos + blk]
+        if len(raw) != blk:                                                # :159
+            break
+        pos += blk
+
+        def replica(off):
+            t = np.linspace(rem_code + off, blk * step + rem_code + off, blk, endpoint=False)
+            return code[np.ceil(t).astype(np.int64)], t
+
+        early, _ = replica(-spc)                                           # :166-172
+        late, _ = replica(+spc)                                            # :174-180
+        t = np.linspace(rem_code, blk * step + rem_code, blk, endpoint=False)
+        prompt = code[np.ceil(t).astype(np.int64)]                         # :182-188
+        rem_code = t[blk - 1] + step - 1023.0                              # :190
+        tm = np.arange(0, blk + 1) / fs                                    # :193
+        arg = carr_freq * 2.0 * np.pi * tm + rem_carr                      # :195
+        rem_carr = arg[blk] % (2 * np.pi)                                  # :197
+        q_bb = np.cos(arg[:blk]) * raw                                     # :199,205
+        i_bb = np.sin(arg[:blk]) * raw                                     # :201,207
+        ie, qe = (early * i_bb).sum(), (early * q_bb).sum()                # :209-211
+        ip, qp = (prompt * i_bb).sum(), (prompt * q_bb).sum()              # :213-215
+        il, ql = (late * i_bb).sum(), (late * q_bb).sum()                  # :217-219
+        with np.errstate(divide="ignore", invalid="ignore"):
+            carr_err = np.arctan(qp / ip) / 2.0 / np.pi                    # :223
+        carr_nco = old_carr_nco + t2p / t1p * (carr_err - old_carr_err) + carr_err * (pdi / t1p)
+        old_carr_nco, old_carr_err = carr_nco, carr_err                    # :225-231
+        carr_freq = carr_basis + carr_nco                                  # :233
+        e_mag = np.sqrt(ie * ie + qe * qe)
+        l_mag = np.sqrt(il * il + ql * ql)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            code_err = (e_mag - l_mag) / (e_mag + l_mag)                   # :238
+        code_nco = old_code_nco + t2c / t1c * (code_err - old_code_err) + code_err * (pdi / t1c)
+        old_code_nco, old_code_err = code_nco, code_err                    # :241-247
+        code_freq = s.codeFreqBasis - code_nco                             # :249
+        out["absoluteSample"][k] = pos                                     # :255 (fid.tell())
+        out["codeFreq"][k] = code_freq
+        out["carrFreq"][k] = carr_freq
+        out["dllDiscr"][k] = code_err
+        out["dllDiscrFilt"][k] = code_nco
+        out["pllDiscr"][k] = carr_err
+        out["pllDiscrFilt"][k] = carr_nco
+        out["I_E"][k], out["I_P"][k], out["I_L"][k] = ie, ip, il
+        out["Q_E"][k], out["Q_P"][k], out["Q_L"][k] = qe, qp, ql
+        done += 1
+    return out, done
+
+
+def track(data, channels, s, ms=None):
+    """tracking.py:59-295 -- list of (PRN, status, series dict) for channels with PRN != 0,
+    or None if any channel hits the short-read exit (tracking.py:159-163)."""
+    recs = []
+    for ch in range(s.numberOfChannels):
+        if channels["PRN"][ch] == 0:                                       # :99
+            continue
+        series, done = track_channel(data, channels["PRN"][ch], channels["acquiredFreq"][ch],
+                                     channels["codePhase"][ch], s, ms)
+        want = int(s.msToProcess) if ms is None else int(ms)
+        if done != want:
+            return None
+        recs.append((int(channels["PRN"][ch]), channels["status"][ch], series))
+    return recs
