@@ -1,0 +1,138 @@
+/* softgnss_b200.h -- C ABI of the B200-native acquisition / tracking hot paths.
+ *
+ * The reference (perrysou/SoftGNSS-python) is pure Python + numpy and has no FFI of its
+ * own; its stage boundary is the pair of methods
+ *     AcquisitionResult.acquire(longSignal)      reference acquisition.py:27-204
+ *     TrackingResult.track(fid)                  reference tracking.py:13-295
+ * and the recarrays they exchange.  These entry points are what a ctypes binding placed
+ * inside those two methods calls instead of the numpy loops (see INTEGRATION.md for the
+ * stub).  Plain pointers and sizes only; every data pointer may be a host pointer or a CUDA
+ * device pointer (detected with cudaPointerGetAttributes) unless stated otherwise; the caller
+ * owns all buffers.  Return value: 0 or a negative sgx_status; sgx_last_error() gives text.
+ * There is no CPU fallback: without a CUDA device every compute call fails with
+ * SGX_ERR_NODEV.
+ */
+#ifndef SOFTGNSS_B200_H
+#define SOFTGNSS_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGX_ABI_VERSION 1
+#define SGX_NUM_PRN 32
+#define SGX_CODE_LEN 1023
+#define SGX_TRACK_FIELDS 13 /* order: absoluteSample codeFreq carrFreq I_P I_E I_L Q_E Q_P Q_L
+                               dllDiscr dllDiscrFilt pllDiscr pllDiscrFilt (tracking.py:286-293) */
+#define SGX_SYNTH_MAX_SATS 12
+
+typedef enum sgx_status {
+  SGX_OK = 0,
+  SGX_ERR_CUDA = -1,   /* a CUDA runtime call failed                                        */
+  SGX_ERR_ARG = -2,    /* bad argument (PRN outside 1..32, sizes, alignment)                 */
+  SGX_ERR_SHORT = -3,  /* recording too short: tracking.py:159-163 "Not able to read ..."   */
+  SGX_ERR_NODEV = -4,  /* no CUDA device                                                     */
+  SGX_ERR_RANGE = -5   /* loop state left the supported range (block size vs staged window)  */
+} sgx_status;
+
+/* Receiver settings, marshalled from the reference's Settings object (initialize.py:80-173).
+ * Derived integers are computed by the host with the reference's float64 expressions. */
+typedef struct sgx_settings {
+  double samplingFreq;         /* initialize.py:107 */
+  double IF;                   /* initialize.py:105 */
+  double codeFreqBasis;        /* initialize.py:109 */
+  double acqSearchBand;        /* kHz, initialize.py:123 */
+  double acqThreshold;         /* initialize.py:126 */
+  double acqDopplerStep;       /* Hz; 500.0 = the literal at acquisition.py:101 */
+  double dllCorrelatorSpacing; /* chips, initialize.py:134 */
+  double tau1code, tau2code;   /* calcLoopCoef(dllNoiseBandwidth, dllDampingRatio, 1.0), tracking.py:45 */
+  double tau1carr, tau2carr;   /* calcLoopCoef(pllNoiseBandwidth, pllDampingRatio, 0.25), tracking.py:52 */
+  double PDIcode, PDIcarr;     /* 0.001, tracking.py:42,49 */
+  int64_t skipNumberOfBytes;   /* initialize.py:94 */
+  int32_t codeLength;          /* 1023 */
+  int32_t samplesPerCode;      /* initialize.py:183-185 */
+  int32_t numAcqSatellites;    /* len(acqSatelliteList): PRN 1..n are searched (acquisition.py:92) */
+  int32_t numFrqBins;          /* acquisition.py:68 */
+  int32_t acqCoherentMs;       /* 1 in the reference */
+  int32_t acqNonCoherentBlocks;/* 2 in the reference (pick-max of two blocks, acquisition.py:129-133) */
+  int32_t samplesPerCodeChip;  /* round(fs/codeFreqBasis), acquisition.py:145 */
+  int32_t fineMs;              /* 10, acquisition.py:172-177 */
+  int32_t msToProcess;         /* initialize.py:85 */
+  int32_t numberOfChannels;    /* initialize.py:88 */
+} sgx_settings;
+
+/* One tracking channel as produced by preRun (acquisition.py:278-304). prn == 0: idle. */
+typedef struct sgx_channel {
+  int32_t prn;
+  int32_t reserved;
+  double acquiredFreq;
+  double codePhase;
+} sgx_channel;
+
+/* Integer parameter block of the synthetic recording generator (softgnss_python_b200/synth.py). */
+typedef struct sgx_synth_spec {
+  uint64_t seed;
+  int32_t n_sats;
+  int32_t noise_k;
+  int32_t n_bits;
+  int32_t reserved;
+  int32_t prn[SGX_SYNTH_MAX_SATS];
+  int32_t amp[SGX_SYNTH_MAX_SATS];
+  int32_t per0[SGX_SYNTH_MAX_SATS];
+  uint64_t phi0[SGX_SYNTH_MAX_SATS];
+  uint64_t dphi[SGX_SYNTH_MAX_SATS];
+  uint64_t cp0[SGX_SYNTH_MAX_SATS];
+  uint64_t dcp[SGX_SYNTH_MAX_SATS];
+} sgx_synth_spec;
+
+int sgx_abi_version(void);
+const char* sgx_last_error(void);
+/* Number of CUDA devices (0 if none / driver missing). */
+int sgx_device_count(void);
+int sgx_set_device(int device);
+/* Kernels launched by this library in this process since load (bench.py's gpu_launches). */
+int64_t sgx_kernel_launch_count(void);
+
+/* Replaces the body of AcquisitionResult.acquire (acquisition.py:49-204) for `n_recordings`
+ * independent recordings and the PRN shard [prn_first, prn_first+prn_count) (0-based).
+ *   sig        int8 [n_recordings][rec_stride]; each needs >= (blocks*coh + fineMs... ) i.e. 11 ms
+ *   n_samples  valid samples per recording (the reference passes 11*samplesPerCode)
+ *   ca_table   host int8 [32][samplesPerCode]   = makeCaTable()            (initialize.py:188-231)
+ *   ca_chips   host int8 [32][1023]             = generateCAcode(prn)      (initialize.py:234-302)
+ *   fine_idx   host uint16 [fineMs*samplesPerCode] chip index of acquisition.py:172-174
+ * Outputs (host, [n_recordings][prn_count]): carrFreq/codePhase (0 when not detected),
+ * peakMetric (always), and optional diagnostics (may be NULL): frqBin, finePeakIndex.
+ */
+int sgx_acquire(const int8_t* sig, int64_t rec_stride, int64_t n_samples, int32_t n_recordings,
+                const sgx_settings* st, const int8_t* ca_table, const int8_t* ca_chips,
+                const uint16_t* fine_idx, int32_t prn_first, int32_t prn_count,
+                double* carrFreq, double* codePhase, double* peakMetric,
+                int32_t* frqBin, int32_t* finePeakIndex, void* cuda_stream);
+
+/* Replaces the channel/ms loops of TrackingResult.track (tracking.py:59-283) for
+ * n_recordings x n_channels independent channels.
+ *   rec      int8 [n_recordings][rec_stride], rec_stride % 16 == 0 and the buffer readable up to
+ *            the next multiple of 16 past rec_len[r]
+ *   rec_len  host int64 [n_recordings] valid bytes (the file size)
+ *   ch       host [n_recordings][n_channels]
+ *   out      double [n_recordings][n_channels][SGX_TRACK_FIELDS][ms] (host or device)
+ *   ms_done  host int32 [n_recordings][n_channels] code periods completed
+ * Returns SGX_ERR_SHORT if any active channel ran out of samples (results then cover ms_done).
+ */
+int sgx_track(const int8_t* rec, int64_t rec_stride, const int64_t* rec_len, int32_t n_recordings,
+              const sgx_channel* ch, int32_t n_channels, const sgx_settings* st,
+              const int8_t* ca_chips, double* out, int32_t* ms_done, void* cuda_stream);
+
+/* Synthetic int8 IF recordings, bit-identical to synth.generate_cpu.
+ *   out   int8 [n_recordings][rec_stride] (host or device), samples start .. start+n_samples-1
+ *   bits  host int8 [n_recordings][SGX_SYNTH_MAX_SATS][n_bits] nav bits (+-1)
+ *   lut   host int16 [4096] cosine table, ca_chips host int8 [32][1023]
+ */
+int sgx_synth_generate(int8_t* out, int64_t rec_stride, int64_t n_samples, int64_t start,
+                       int32_t n_recordings, const sgx_synth_spec* specs, const int8_t* bits,
+                       const int16_t* lut, const int8_t* ca_chips, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOFTGNSS_B200_H */

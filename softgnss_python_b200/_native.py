@@ -1,0 +1,154 @@
+"""ctypes binding of the C ABI declared in include/softgnss_b200.h.
+
+The library is the in-tree ``libsoftgnss_b200.so`` built by ``build.py`` (nvcc, sm_100a).  There is
+no CPU fallback: every compute entry point raises :class:`NativeError` when the library or a CUDA
+device is missing.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from .settings import SgxSettings
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsoftgnss_b200.so")
+MAX_SATS = 12
+TRACK_FIELDS = ("absoluteSample", "codeFreq", "carrFreq", "I_P", "I_E", "I_L", "Q_E", "Q_P", "Q_L",
+                "dllDiscr", "dllDiscrFilt", "pllDiscr", "pllDiscrFilt")
+SGX_ERR_SHORT = -3
+
+EXPORTS = ("sgx_abi_version", "sgx_last_error", "sgx_device_count", "sgx_set_device",
+           "sgx_kernel_launch_count", "sgx_acquire", "sgx_track", "sgx_synth_generate")
+
+
+class NativeError(RuntimeError):
+    def __init__(self, code, msg):
+        RuntimeError.__init__(self, "softgnss_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class SgxChannel(ctypes.Structure):
+    _fields_ = [("prn", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("acquiredFreq", ctypes.c_double), ("codePhase", ctypes.c_double)]
+
+
+class SgxSynthSpec(ctypes.Structure):
+    _fields_ = [("seed", ctypes.c_uint64), ("n_sats", ctypes.c_int32), ("noise_k", ctypes.c_int32),
+                ("n_bits", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("prn", ctypes.c_int32 * MAX_SATS), ("amp", ctypes.c_int32 * MAX_SATS),
+                ("per0", ctypes.c_int32 * MAX_SATS),
+                ("phi0", ctypes.c_uint64 * MAX_SATS), ("dphi", ctypes.c_uint64 * MAX_SATS),
+                ("cp0", ctypes.c_uint64 * MAX_SATS), ("dcp", ctypes.c_uint64 * MAX_SATS)]
+
+
+def _ptr(x):
+    """Raw address of a numpy array, a torch tensor, a ctypes object or an int."""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return ctypes.c_void_p(x)
+    if isinstance(x, np.ndarray):
+        assert x.flags["C_CONTIGUOUS"]
+        return ctypes.c_void_p(x.ctypes.data)
+    if hasattr(x, "data_ptr"):
+        return ctypes.c_void_p(x.data_ptr())
+    return ctypes.cast(x, ctypes.c_void_p)
+
+
+class Lib(object):
+    def __init__(self, path=LIB_PATH):
+        if not os.path.exists(path):
+            raise NativeError(-100, "%s not built -- run `python -m softgnss_python_b200.build` "
+                                    "(needs nvcc; there is no CPU fallback)" % path)
+        self.path = path
+        self.dll = ctypes.CDLL(path)
+        vp, i32, i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
+        d = self.dll
+        d.sgx_abi_version.restype = ctypes.c_int
+        d.sgx_last_error.restype = ctypes.c_char_p
+        d.sgx_device_count.restype = ctypes.c_int
+        d.sgx_set_device.argtypes = [ctypes.c_int]
+        d.sgx_kernel_launch_count.restype = i64
+        d.sgx_track.argtypes = [vp, i64, vp, i32, vp, i32, ctypes.POINTER(SgxSettings), vp, vp, vp, vp]
+        d.sgx_synth_generate.argtypes = [vp, i64, i64, i64, i32, vp, vp, vp, vp, vp]
+        if hasattr(d, "sgx_acquire"):
+            d.sgx_acquire.argtypes = [vp, i64, i64, i32, ctypes.POINTER(SgxSettings), vp, vp, vp, i32, i32,
+                                      vp, vp, vp, vp, vp, vp]
+
+    def check(self, rc):
+        if rc != 0:
+            raise NativeError(rc, self.dll.sgx_last_error().decode())
+
+    def require_device(self):
+        if self.dll.sgx_device_count() <= 0:
+            raise NativeError(-4, "no CUDA device visible; the B200 path has no CPU fallback")
+
+    def launches(self):
+        return int(self.dll.sgx_kernel_launch_count())
+
+    # ------------------------------------------------------------------ tracking
+    def track(self, rec, rec_stride, rec_len, channels, pod, ca_chips, out, stream=0):
+        """rec: int8 numpy [R, stride] / torch cuda tensor / address; channels: SgxChannel array [R*C];
+        out: float64 numpy or cuda tensor [R, C, 13, ms].  Returns (rc, ms_done[R, C])."""
+        self.require_device()
+        rec_len = np.ascontiguousarray(rec_len, dtype=np.int64)
+        r = len(rec_len)
+        c = len(channels) // r
+        ms_done = np.zeros((r, c), dtype=np.int32)
+        rc = self.dll.sgx_track(_ptr(rec), int(rec_stride), _ptr(rec_len), r, _ptr(channels), c,
+                                ctypes.byref(pod), _ptr(ca_chips), _ptr(out), _ptr(ms_done),
+                                ctypes.c_void_p(stream))
+        return rc, ms_done
+
+    # ------------------------------------------------------------------ synthetic recordings
+    def synth(self, out, rec_stride, n_samples, start, specs, bits, lut, ca_chips, stream=0):
+        self.require_device()
+        self.check(self.dll.sgx_synth_generate(_ptr(out), int(rec_stride), int(n_samples), int(start),
+                                               len(specs), _ptr(specs), _ptr(bits), _ptr(lut),
+                                               _ptr(ca_chips), ctypes.c_void_p(stream)))
+
+
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = Lib()
+    return _LIB
+
+
+def ca_chips_int8():
+    from .settings import ca_code_bits
+    return np.ascontiguousarray(np.stack([ca_code_bits(p) for p in range(32)]).astype(np.int8) * 2 - 1)
+
+
+def make_channels(prn, freq, cph):
+    n = len(prn)
+    arr = (SgxChannel * n)()
+    for i in range(n):
+        arr[i].prn = int(prn[i])
+        arr[i].acquiredFreq = float(freq[i])
+        arr[i].codePhase = float(cph[i])
+    return arr
+
+
+def make_synth_specs(specs):
+    """list of synth.RecordingSpec -> (SgxSynthSpec array, bits int8 [R, MAX_SATS, n_bits])."""
+    n = len(specs)
+    arr = (SgxSynthSpec * n)()
+    nb = specs[0].n_bits
+    bits = np.ones((n, MAX_SATS, nb), dtype=np.int8)
+    for r, sp in enumerate(specs):
+        a = arr[r]
+        a.seed = sp.seed & ((1 << 64) - 1)
+        a.n_sats = len(sp.prn)
+        a.noise_k = sp.noise_k
+        a.n_bits = nb
+        for i in range(len(sp.prn)):
+            a.prn[i] = int(sp.prn[i]); a.amp[i] = int(sp.amp[i]); a.per0[i] = int(sp.per0[i])
+            a.phi0[i] = int(sp.phi0[i]); a.dphi[i] = int(sp.dphi[i])
+            a.cp0[i] = int(sp.cp0[i]); a.dcp[i] = int(sp.dcp[i])
+        bits[r, :len(sp.prn)] = sp.bits
+    return arr, bits

@@ -1,0 +1,50 @@
+"""Compile the CUDA sources in csrc/ into the in-tree shared library (sm_100a only).
+
+    python -m softgnss_python_b200.build
+
+``-fmad=false``: float64 loop-filter / code-phase arithmetic must round every operation
+separately, as numpy does; hot float32 loops call fmaf() explicitly.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libsoftgnss_b200.so")
+SOURCES = ["sgx_api.cu", "sgx_track.cu", "sgx_synth.cu", "sgx_acq.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-fmad=false", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--use_fast_math=false"]
+
+
+def _sources():
+    return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = _sources() + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+    deps.append(os.path.join(os.path.dirname(HERE), "include", "softgnss_b200.h"))
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_native(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
+    cmd = [nvcc] + flags + ["-shared", "-o", LIB] + _sources()
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    with open(os.path.join(HERE, "csrc", "ptxas_report.txt"), "w") as f:
+        f.write(res.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_native(force=True, verbose="-v" in sys.argv))

@@ -1,0 +1,139 @@
+// Shared plumbing of the sm_100a sources: launch macro, error capture, async-copy helpers.
+#pragma once
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#ifdef SGX_EMUL
+#include "cuda_emul.h"  // tools/cpu_emul: developer-only CPU single-stepping, never shipped
+#else
+#include <cuda_runtime.h>
+#define SGX_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define SGX_DYN_SMEM(name) extern __shared__ __align__(1024) unsigned char name[]
+#endif
+
+#include "../../include/softgnss_b200.h"
+
+namespace sgx {
+
+extern char g_err[512];
+extern long long g_launches;
+
+inline int fail(int code, const char* what, const char* detail) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", what, detail ? detail : "");
+  return code;
+}
+
+#define SGX_CUDA(call)                                                          \
+  do {                                                                          \
+    cudaError_t e__ = (call);                                                   \
+    if (e__ != cudaSuccess) return sgx::fail(SGX_ERR_CUDA, #call, cudaGetErrorString(e__)); \
+  } while (0)
+
+#define SGX_COUNTED_LAUNCH(...)  \
+  do {                           \
+    SGX_LAUNCH(__VA_ARGS__);     \
+    ++sgx::g_launches;           \
+  } while (0)
+
+inline bool is_device_ptr(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// Scratch device buffer that only ever grows (plans keep them for the process lifetime).
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t n) {
+    if (n <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    if (cudaMalloc(&p, n) != cudaSuccess) return -1;
+    cap = n;
+    return 0;
+  }
+  template <class T> T* as() { return (T*)p; }
+};
+
+// ---- Ampere-style 16-byte async copy global -> shared (LDGSTS) ------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+#ifdef SGX_EMUL
+  memcpy(smem_dst, gsrc, 16);
+#else
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_commit() {
+#ifndef SGX_EMUL
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+#ifndef SGX_EMUL
+  asm volatile("cp.async.wait_all;\n" ::: "memory");
+#endif
+}
+
+// ---- TMA 1-D bulk copy global -> shared completing on an mbarrier (UBLKCP in SASS) ----------
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+#ifdef SGX_EMUL
+  *bar = 0;
+  (void)count;
+#else
+  unsigned s = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(s), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+#endif
+}
+// one thread: arm the barrier with the byte count and start the copy (bytes % 16 == 0, both 16B-aligned)
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, unsigned bytes,
+                                          unsigned long long* bar) {
+#ifdef SGX_EMUL
+  memcpy(smem_dst, gsrc, bytes);
+  *bar += 1;  // completed phases
+#else
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(d),
+      "l"(gsrc), "r"(bytes), "r"(b)
+      : "memory");
+#endif
+}
+// all threads: wait until phase `parity` of the barrier has completed
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+#ifdef SGX_EMUL
+  (void)bar;
+  (void)parity;  // bulk_load completed synchronously
+#else
+  unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(b),
+      "r"(parity)
+      : "memory");
+#endif
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+  return v;
+}
+
+}  // namespace sgx

@@ -1,0 +1,503 @@
+// Tracking hot path: one CTA per (recording, channel), the whole millisecond loop on the device.
+//
+// Replaces reference tracking.py:59-283.  Per code period ("ms") the reference
+//   T3  sizes the block from the code NCO            tracking.py:148-151
+//   T4  builds early/late/prompt replicas            tracking.py:166-188   (float64 ceil of a linspace)
+//   T5  carries the code phase                       tracking.py:190
+//   T6  builds sin/cos of the carrier NCO            tracking.py:193-201
+//   T7  mixes and forms six correlator sums          tracking.py:205-219
+//   T8  Costas PLL discriminator + loop filter       tracking.py:223-235
+//   T9  normalised early-late DLL + loop filter      tracking.py:238-251
+//   T10 records 13 values                            tracking.py:255-275
+//
+// Device formulation (DESIGN.md section "K5"):
+//  * the block of int8 samples is staged in shared memory one period ahead (TMA 1-D bulk copy
+//    completing on an mbarrier, or 16-byte cp.async), double buffered;
+//  * each thread owns a contiguous run of 16-sample groups.  The carrier is e^{j theta_i} =
+//    rot_g * w^k (k = 0..15): sixteen per-period twiddles w^k live in registers, rot_g advances by
+//    w^16 per group, so a sample costs one byte->float conversion and two FMAs;
+//  * the replicas are piecewise constant (one chip = 37.3 samples): every thread walks the chip
+//    boundaries ("events") of E, P and L inside its run.  An event index is predicted in float64
+//    from the reference's own linspace parameters and, when the prediction is within 1e-6 of an
+//    integer, settled by evaluating the reference's expression fl(fl(i*step)+start) exactly, so
+//    the sample->chip assignment equals ceil(tcode) of the reference for every sample;
+//  * a group is summed in two halves split at the (at most one) event position, the halves are
+//    rotated once and added with the code signs -> 6 running sums per thread, warp shuffle,
+//    one shared-memory exchange;
+//  * thread 0 then runs T8/T9/T5/T3 in float64 with separately rounded operations (compiled with
+//    -fmad=false) exactly in the reference's order and publishes the next period's parameters.
+#include "sgx_common.cuh"
+
+namespace sgx {
+
+constexpr int TRK_THREADS = 256;
+constexpr int TRK_WARPS = TRK_THREADS / 32;
+constexpr int TRK_MARGIN = 256;  // extra samples staged beyond samplesPerCode
+
+struct TrackArgs {
+  const int8_t* rec;
+  long long rec_stride;
+  const long long* rec_len;
+  const sgx_channel* ch;
+  const int8_t* chips;  // [32][1023] +-1
+  double* out;          // [R*C][13][ms]
+  int* ms_done;         // [R*C]
+  int* status;          // [R*C] sgx_status of the channel
+  int n_channels;
+  int ms;
+  int win;              // bytes per staging buffer, multiple of 16
+  long long skip;
+  double fs, codeFreqBasis, codeLength, spc;
+  double c1code, c2code, c1carr, c2carr;  // tau2/tau1 and PDI/tau1 (tracking.py:225-227, 241-243)
+};
+
+struct MsParams {
+  double startE, stepE, startL, stepL, startP, stepP;  // np.linspace(start, ., blk, endpoint=False)
+  double inv_step;  // 1/codePhaseStep, used only to *predict* event indices
+  double cps;       // carrier cycles per sample
+  double rem_cyc;   // remCarrPhase in cycles
+  long long pos;    // byte offset (within the recording) of sample 0 of this block
+  int blk;
+  int stop;         // 0 = run this period, else sgx_status / 1 = finished
+};
+
+// thread-0 loop state (tracking.py:114-130)
+struct LoopState {
+  double codeFreq, remCodePhase, carrFreq, carrFreqBasis, remCarrPhase;
+  double oldCodeNco, oldCodeError, oldCarrNco, oldCarrError;
+  long long pos;
+};
+
+__device__ __forceinline__ double lin_y(int i, double step, double start) {
+  // element i of np.linspace: two roundings, multiply then add (no FMA)
+  return __dadd_rn(__dmul_rn((double)i, step), start);
+}
+
+// First sample index whose replica index exceeds c, i.e. first i with fl(fl(i*step)+start) > c.
+__device__ __forceinline__ int next_event(int c, double start, double step, double inv) {
+  double q = ((double)c - start) * inv;
+  double fl = floor(q);
+  int i = (int)fl + 1;
+  double fr = q - fl;
+  if (fr < 1e-6 || fr > 1.0 - 1e-6) {
+    while (i > 0 && lin_y(i - 1, step, start) > (double)c) --i;
+    while (!(lin_y(i, step, start) > (double)c)) ++i;
+  }
+  return i;
+}
+
+struct CodeVar {
+  double start, step;
+  int c;    // index into the padded code (tracking.py:111) for the current sample
+  int e;    // first sample index at which the index becomes c+1
+  float s;  // code value +-1 at c
+  __device__ __forceinline__ void init(int i0, double st, double sp, double inv, const float* code) {
+    start = st;
+    step = sp;
+    c = (int)ceil(lin_y(i0, step, start));
+    s = code[c];
+    e = next_event(c, start, step, inv);
+  }
+  __device__ __forceinline__ void advance(double inv, const float* code) {
+    c += 1;
+    s = code[c];
+    e = next_event(c, start, step, inv);
+  }
+};
+
+__device__ __forceinline__ float byte_to_float(unsigned u_offset_binary, int k) {
+  // u = x ^ 0x80 per byte; 0x4B0000uu is the float 2^23 + uu
+  unsigned r = __byte_perm(u_offset_binary, 0x4B000000u, 0x7540u + (unsigned)k);
+  return __uint_as_float(r) - 8388736.0f;
+}
+
+__device__ __forceinline__ void cmul(float& r, float& i, float ar, float ai, float br, float bi) {
+  r = fmaf(ar, br, -(ai * bi));
+  i = fmaf(ar, bi, ai * br);
+}
+
+// T3 + T4 parameters + T5/T6 carries for the next period, evaluated by thread 0 in float64.
+__device__ void prepare_period(const TrackArgs& a, LoopState& st, long long rec_len, MsParams& p,
+                               double& nextRemCode, double& nextRemCarr) {
+  const double TWO_PI = 6.283185307179586;  // == 2*np.pi
+  const double PI = 3.141592653589793;
+  double step = st.codeFreq / a.fs;                                   // :148
+  int blk = (int)ceil((a.codeLength - st.remCodePhase) / step);       // :150
+  p.blk = blk;
+  p.pos = st.pos;
+  p.stop = 0;
+  long long aligned = st.pos & ~15LL;
+  if (st.pos + blk > rec_len) { p.stop = SGX_ERR_SHORT; return; }     // :159
+  if (blk <= 0 || (st.pos - aligned) + blk > a.win) { p.stop = SGX_ERR_RANGE; return; }
+  double rem = st.remCodePhase, spc = a.spc, bs = (double)blk * step;
+  p.startE = rem - spc;                                               // :166
+  p.stepE = (((bs + rem) - spc) - p.startE) / (double)blk;
+  p.startL = rem + spc;                                               // :174
+  p.stepL = (((bs + rem) + spc) - p.startL) / (double)blk;
+  p.startP = rem;                                                     // :182
+  p.stepP = ((bs + rem) - p.startP) / (double)blk;
+  p.inv_step = 1.0 / step;
+  nextRemCode = (lin_y(blk - 1, p.stepP, p.startP) + step) - 1023.0;  // :190
+  double w = st.carrFreq * 2.0 * PI;                                  // :195
+  double arg_end = w * ((double)blk / a.fs) + st.remCarrPhase;
+  double m = fmod(arg_end, TWO_PI);                                   // :197 (np.remainder)
+  if (m != 0.0 && m < 0.0) m += TWO_PI;
+  nextRemCarr = m;
+  p.cps = (w / a.fs) * 0.15915494309189535;
+  p.rem_cyc = st.remCarrPhase * 0.15915494309189535;
+}
+
+template <bool BULK>
+__global__ void __launch_bounds__(TRK_THREADS, 2) track_kernel(TrackArgs a) {
+  SGX_DYN_SMEM(smem);
+  int8_t* buf0 = (int8_t*)smem;
+  int8_t* buf1 = buf0 + a.win;
+  __shared__ MsParams prm;
+  __shared__ float red[TRK_WARPS][6];
+  __shared__ float codeS[1040];  // 1025 used; the tail absorbs indices reached only by masked samples
+  __shared__ unsigned long long mbar[2];
+
+  const int tid = threadIdx.x;
+  const int cid = blockIdx.x;  // recording * n_channels + channel
+  const int rid = cid / a.n_channels;
+  const sgx_channel chn = a.ch[cid];
+  if (chn.prn == 0) {  // tracking.py:99 -- idle channel, no record
+    if (tid == 0) { a.ms_done[cid] = 0; a.status[cid] = SGX_OK; }
+    return;
+  }
+  const int8_t* rec = a.rec + (long long)rid * a.rec_stride;
+  const long long rec_len = a.rec_len[rid];
+  const long long rec_alloc = (rec_len + 15) & ~15LL;
+  {  // padded code [c1022, c0..c1022, c0] (tracking.py:109-111)
+    const int8_t* c = a.chips + (chn.prn - 1) * 1023;
+    for (int i = tid; i < 1040; i += TRK_THREADS) codeS[i] = i < 1025 ? (float)c[(i + 1022) % 1023] : 0.f;
+  }
+  LoopState st;
+  double nextRemCode = 0.0, nextRemCarr = 0.0;
+  if (tid == 0) {
+    st.codeFreq = a.codeFreqBasis;          // :114
+    st.remCodePhase = 0.0;
+    st.carrFreq = chn.acquiredFreq;         // :118
+    st.carrFreqBasis = chn.acquiredFreq;
+    st.remCarrPhase = 0.0;
+    st.oldCodeNco = st.oldCodeError = st.oldCarrNco = st.oldCarrError = 0.0;
+    st.pos = a.skip + (long long)chn.codePhase;  // :107
+    prepare_period(a, st, rec_len, prm, nextRemCode, nextRemCarr);
+    if (BULK) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); }
+  }
+  __syncthreads();
+
+  // stage the window of period 0
+  auto stage = [&](int8_t* dst, long long pos) {
+    long long al = pos & ~15LL;
+    long long nb = rec_alloc - al;
+    if (nb > a.win) nb = a.win;
+    if (nb <= 0) return 0;
+    if (BULK) {
+      return (int)nb;
+    } else {
+      const int8_t* src = rec + al;
+      for (int o = tid * 16; o < (int)nb; o += TRK_THREADS * 16) cp_async16(dst + o, src + o);
+      cp_async_commit();
+      return (int)nb;
+    }
+  };
+  unsigned phase0 = 0, phase1 = 0;  // mbarrier phase parity per buffer
+  bool pending0 = false, pending1 = false;
+  if (prm.stop == 0) {
+    int nb = stage(buf0, prm.pos);
+    if (BULK) {
+      if (nb > 0) {
+        if (tid == 0) bulk_load(buf0, rec + (prm.pos & ~15LL), (unsigned)nb, &mbar[0]);
+        pending0 = true;
+      }
+    }
+  }
+
+  int k = 0;
+  for (; k < a.ms; ++k) {
+    const MsParams P = prm;
+    if (P.stop != 0) break;
+    int8_t* cur = (k & 1) ? buf1 : buf0;
+    int8_t* nxt = (k & 1) ? buf0 : buf1;
+    // ---- make this period's samples visible ------------------------------------------------
+    if (BULK) {
+      if (k & 1) { if (pending1) { mbar_wait(&mbar[1], phase1); phase1 ^= 1; pending1 = false; } }
+      else       { if (pending0) { mbar_wait(&mbar[0], phase0); phase0 ^= 1; pending0 = false; } }
+    } else {
+      if (k == 0) { cp_async_wait_all(); __syncthreads(); }
+    }
+    // ---- prefetch the next period's window -------------------------------------------------
+    {
+      long long npos = P.pos + P.blk;
+      int nb = stage(nxt, npos);
+      if (BULK && nb > 0) {
+        if (tid == 0) bulk_load(nxt, rec + (npos & ~15LL), (unsigned)nb, &mbar[(k + 1) & 1]);
+        if (k & 1) pending0 = true; else pending1 = true;
+      }
+    }
+
+    // ---- correlate: contiguous run of 16-sample groups per thread --------------------------
+    const int off = (int)(P.pos - (P.pos & ~15LL));
+    const int ng = (off + P.blk + 15) >> 4;
+    const int gpt = (ng + TRK_THREADS - 1) / TRK_THREADS;
+    const int g0 = tid * gpt;
+    const int g1 = min(g0 + gpt, ng);
+    float tEr = 0.f, tEi = 0.f, tPr = 0.f, tPi = 0.f, tLr = 0.f, tLi = 0.f;
+    if (g0 < g1) {
+      int ib = 16 * g0 - off;
+      const int i0 = max(ib, 0);
+      CodeVar E, Pm, L;
+      E.init(i0, P.startE, P.stepE, P.inv_step, codeS);
+      Pm.init(i0, P.startP, P.stepP, P.inv_step, codeS);
+      L.init(i0, P.startL, P.stepL, P.inv_step, codeS);
+      // carrier: rot = e^{j theta(ib)}, w[k] = e^{j k dtheta}
+      float wr[16], wi[16], w16r, w16i, rotr, roti;
+      {
+        double ph = (double)ib * P.cps + P.rem_cyc;
+        ph -= rint(ph);
+        sincospif(2.0f * (float)ph, &roti, &rotr);
+        double d1 = P.cps - rint(P.cps);
+        float s1, c1;
+        sincospif(2.0f * (float)d1, &s1, &c1);
+        wr[0] = 1.f; wi[0] = 0.f; wr[1] = c1; wi[1] = s1;
+#pragma unroll
+        for (int q = 2; q < 16; ++q) {
+          // w^q from the two closest already-known powers keeps the error at a few ulp
+          cmul(wr[q], wi[q], wr[q >> 1], wi[q >> 1], wr[q - (q >> 1)], wi[q - (q >> 1)]);
+        }
+        double d16 = 16.0 * P.cps;
+        d16 -= rint(d16);
+        sincospif(2.0f * (float)d16, &w16i, &w16r);
+      }
+      for (int g = g0; g < g1; ++g, ib += 16) {
+        uint4 q4 = *reinterpret_cast<const uint4*>(cur + 16 * g);
+        unsigned wq[4] = {q4.x, q4.y, q4.z, q4.w};
+        if (ib < 0 || ib + 16 > P.blk) {  // head / tail of the block: zero the foreign samples
+#pragma unroll
+          for (int b = 0; b < 16; ++b) {
+            int i = ib + b;
+            if (i < 0 || i >= P.blk) wq[b >> 2] &= ~(0xFFu << (8 * (b & 3)));
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) wq[j] ^= 0x80808080u;
+        const int kE = E.e - ib, kP = Pm.e - ib, kL = L.e - ib;
+        const int kb = min(min(kE, kP), min(kL, 16));
+        // tentative state after the event(s) at kb
+        CodeVar E2 = E, P2 = Pm, L2 = L;
+        if (kE == kb) E2.advance(P.inv_step, codeS);
+        if (kP == kb) P2.advance(P.inv_step, codeS);
+        if (kL == kb) L2.advance(P.inv_step, codeS);
+        const bool single = (E2.e - ib >= 16) && (P2.e - ib >= 16) && (L2.e - ib >= 16);
+        if (single) {
+          float Ar = 0.f, Ai = 0.f, Br = 0.f, Bi = 0.f;
+#pragma unroll
+          for (int b = 0; b < 16; ++b) {
+            float x = byte_to_float(wq[b >> 2], b & 3);
+            if (b < kb) { Ar = fmaf(x, wr[b], Ar); Ai = fmaf(x, wi[b], Ai); }
+            else        { Br = fmaf(x, wr[b], Br); Bi = fmaf(x, wi[b], Bi); }
+          }
+          float RAr, RAi, RBr, RBi;
+          cmul(RAr, RAi, rotr, roti, Ar, Ai);
+          cmul(RBr, RBi, rotr, roti, Br, Bi);
+          tEr = fmaf(E.s, RAr, tEr); tEi = fmaf(E.s, RAi, tEi);
+          tPr = fmaf(Pm.s, RAr, tPr); tPi = fmaf(Pm.s, RAi, tPi);
+          tLr = fmaf(L.s, RAr, tLr); tLi = fmaf(L.s, RAi, tLi);
+          tEr = fmaf(E2.s, RBr, tEr); tEi = fmaf(E2.s, RBi, tEi);
+          tPr = fmaf(P2.s, RBr, tPr); tPi = fmaf(P2.s, RBi, tPi);
+          tLr = fmaf(L2.s, RBr, tLr); tLi = fmaf(L2.s, RBi, tLi);
+          E = E2; Pm = P2; L = L2;
+        } else {
+          // several chip boundaries inside one group (low sampling rates, or E/L boundaries that
+          // round to neighbouring samples): sample-by-sample walk
+          float rr = rotr, ri = roti;
+#pragma unroll
+          for (int b = 0; b < 16; ++b) {
+            const int i = ib + b;
+            while (E.e <= i) E.advance(P.inv_step, codeS);
+            while (Pm.e <= i) Pm.advance(P.inv_step, codeS);
+            while (L.e <= i) L.advance(P.inv_step, codeS);
+            float x = byte_to_float(wq[b >> 2], b & 3);
+            float pr = x * rr, pi = x * ri;
+            tEr = fmaf(E.s, pr, tEr); tEi = fmaf(E.s, pi, tEi);
+            tPr = fmaf(Pm.s, pr, tPr); tPi = fmaf(Pm.s, pi, tPi);
+            tLr = fmaf(L.s, pr, tLr); tLi = fmaf(L.s, pi, tLi);
+            float nr, ni;
+            cmul(nr, ni, rr, ri, wr[1], wi[1]);
+            rr = nr; ri = ni;
+          }
+          // bring the state to the first sample of the next group
+          while (E.e <= ib + 15) E.advance(P.inv_step, codeS);
+          while (Pm.e <= ib + 15) Pm.advance(P.inv_step, codeS);
+          while (L.e <= ib + 15) L.advance(P.inv_step, codeS);
+        }
+        float nr, ni;
+        cmul(nr, ni, rotr, roti, w16r, w16i);
+        rotr = nr; roti = ni;
+      }
+    }
+    // I arm = sin (imaginary part), Q arm = cos (real part): tracking.py:205-207
+    float v0 = warp_sum(tEi), v1 = warp_sum(tEr), v2 = warp_sum(tPi), v3 = warp_sum(tPr),
+          v4 = warp_sum(tLi), v5 = warp_sum(tLr);
+    if ((tid & 31) == 0) {
+      float* r = red[tid >> 5];
+      r[0] = v0; r[1] = v1; r[2] = v2; r[3] = v3; r[4] = v4; r[5] = v5;
+    }
+    if (!BULK) cp_async_wait_all();
+    __syncthreads();
+    if (tid == 0) {
+      double s[6];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        double acc = 0.0;
+        for (int w = 0; w < TRK_WARPS; ++w) acc += (double)red[w][j];
+        s[j] = acc;
+      }
+      const double I_E = s[0], Q_E = s[1], I_P = s[2], Q_P = s[3], I_L = s[4], Q_L = s[5];
+      st.remCodePhase = nextRemCode;
+      st.remCarrPhase = nextRemCarr;
+      st.pos = P.pos + P.blk;
+      // PLL (tracking.py:223-235)
+      double carrError = atan(Q_P / I_P) / 2.0 / 3.141592653589793;
+      double carrNco = st.oldCarrNco + a.c1carr * (carrError - st.oldCarrError) + carrError * a.c2carr;
+      st.oldCarrNco = carrNco;
+      st.oldCarrError = carrError;
+      st.carrFreq = st.carrFreqBasis + carrNco;
+      // DLL (tracking.py:238-251)
+      double em = sqrt(I_E * I_E + Q_E * Q_E), lm = sqrt(I_L * I_L + Q_L * Q_L);
+      double codeError = (em - lm) / (em + lm);
+      double codeNco = st.oldCodeNco + a.c1code * (codeError - st.oldCodeError) + codeError * a.c2code;
+      st.oldCodeNco = codeNco;
+      st.oldCodeError = codeError;
+      st.codeFreq = a.codeFreqBasis - codeNco;
+      // record (tracking.py:255-275)
+      double* o = a.out + (long long)cid * SGX_TRACK_FIELDS * a.ms + k;
+      const long long m = a.ms;
+      o[0 * m] = (double)st.pos;  // fid.tell() after the read
+      o[1 * m] = st.codeFreq;
+      o[2 * m] = st.carrFreq;
+      o[3 * m] = I_P; o[4 * m] = I_E; o[5 * m] = I_L;
+      o[6 * m] = Q_E; o[7 * m] = Q_P; o[8 * m] = Q_L;
+      o[9 * m] = codeError; o[10 * m] = codeNco; o[11 * m] = carrError; o[12 * m] = carrNco;
+      if (k + 1 < a.ms) prepare_period(a, st, rec_len, prm, nextRemCode, nextRemCarr);
+    }
+    __syncthreads();
+  }
+  if (BULK) {  // never exit with a bulk copy in flight
+    if (pending0) mbar_wait(&mbar[0], phase0);
+    if (pending1) mbar_wait(&mbar[1], phase1);
+  } else {
+    cp_async_wait_all();
+  }
+  if (tid == 0) {
+    a.ms_done[cid] = k;
+    a.status[cid] = (k == a.ms) ? SGX_OK : prm.stop;
+  }
+}
+
+// --------------------------------------------------------------------------- host entry
+struct TrackScratch {
+  DevBuf rec, len, ch, chips, out, done, status;
+};
+static TrackScratch g_trk;
+
+static bool use_bulk() {
+  const char* e = getenv("SGX_TRK_STAGE");
+  return !(e && strcmp(e, "cpasync") == 0);
+}
+
+}  // namespace sgx
+
+using namespace sgx;
+
+extern "C" int sgx_track(const int8_t* rec, int64_t rec_stride, const int64_t* rec_len,
+                         int32_t n_recordings, const sgx_channel* ch, int32_t n_channels,
+                         const sgx_settings* st, const int8_t* ca_chips, double* out,
+                         int32_t* ms_done, void* cuda_stream) {
+  if (sgx_device_count() <= 0) return fail(SGX_ERR_NODEV, "sgx_track", "no CUDA device");
+  if (!rec || !rec_len || !ch || !st || !ca_chips || !out || !ms_done || n_recordings <= 0 ||
+      n_channels <= 0 || st->msToProcess <= 0)
+    return fail(SGX_ERR_ARG, "sgx_track", "null pointer or empty problem");
+  const int nch = n_recordings * n_channels;
+  for (int i = 0; i < nch; ++i)
+    if (ch[i].prn < 0 || ch[i].prn > SGX_NUM_PRN) return fail(SGX_ERR_ARG, "sgx_track", "PRN outside 0..32");
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  const int ms = st->msToProcess;
+  const int win = ((st->samplesPerCode + TRK_MARGIN + 15) & ~15) + 16;
+
+  const int8_t* d_rec = rec;
+  long long stride = rec_stride;
+  if (!is_device_ptr(rec)) {  // host recording: stage it in HBM once (the np.fromfile replacement)
+    long long mx = 0;
+    for (int r = 0; r < n_recordings; ++r) mx = rec_len[r] > mx ? rec_len[r] : mx;
+    stride = (mx + 15) & ~15LL;
+    if (g_trk.rec.reserve((size_t)stride * n_recordings + 16)) return fail(SGX_ERR_CUDA, "cudaMalloc", "recording");
+    for (int r = 0; r < n_recordings; ++r)
+      SGX_CUDA(cudaMemcpyAsync(g_trk.rec.as<int8_t>() + (size_t)r * stride, rec + (size_t)r * rec_stride,
+                               (size_t)rec_len[r], cudaMemcpyHostToDevice, s));
+    d_rec = g_trk.rec.as<int8_t>();
+  } else if ((rec_stride & 15) || ((uintptr_t)rec & 15)) {
+    return fail(SGX_ERR_ARG, "sgx_track", "device recordings must be 16-byte aligned with a stride multiple of 16");
+  }
+  if (g_trk.len.reserve(sizeof(long long) * n_recordings) || g_trk.ch.reserve(sizeof(sgx_channel) * nch) ||
+      g_trk.chips.reserve(32 * 1023) || g_trk.done.reserve(sizeof(int) * nch) ||
+      g_trk.status.reserve(sizeof(int) * nch))
+    return fail(SGX_ERR_CUDA, "cudaMalloc", "tracking scratch");
+  SGX_CUDA(cudaMemcpyAsync(g_trk.len.p, rec_len, sizeof(long long) * n_recordings, cudaMemcpyHostToDevice, s));
+  SGX_CUDA(cudaMemcpyAsync(g_trk.ch.p, ch, sizeof(sgx_channel) * nch, cudaMemcpyHostToDevice, s));
+  SGX_CUDA(cudaMemcpyAsync(g_trk.chips.p, ca_chips, 32 * 1023, cudaMemcpyHostToDevice, s));
+  const size_t out_bytes = sizeof(double) * (size_t)nch * SGX_TRACK_FIELDS * ms;
+  double* d_out = out;
+  const bool out_on_host = !is_device_ptr(out);
+  if (out_on_host) {
+    if (g_trk.out.reserve(out_bytes)) return fail(SGX_ERR_CUDA, "cudaMalloc", "tracking output");
+    d_out = g_trk.out.as<double>();
+  }
+
+  TrackArgs a;
+  a.rec = d_rec;
+  a.rec_stride = stride;
+  a.rec_len = g_trk.len.as<long long>();
+  a.ch = g_trk.ch.as<sgx_channel>();
+  a.chips = g_trk.chips.as<int8_t>();
+  a.out = d_out;
+  a.ms_done = g_trk.done.as<int>();
+  a.status = g_trk.status.as<int>();
+  a.n_channels = n_channels;
+  a.ms = ms;
+  a.win = win;
+  a.skip = st->skipNumberOfBytes;
+  a.fs = st->samplingFreq;
+  a.codeFreqBasis = st->codeFreqBasis;
+  a.codeLength = (double)st->codeLength;
+  a.spc = st->dllCorrelatorSpacing;
+  a.c1code = st->tau2code / st->tau1code;
+  a.c2code = st->PDIcode / st->tau1code;
+  a.c1carr = st->tau2carr / st->tau1carr;
+  a.c2carr = st->PDIcarr / st->tau1carr;
+
+  const size_t smem = 2 * (size_t)win;
+  if (use_bulk()) {
+    auto kfn = track_kernel<true>;
+    SGX_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SGX_COUNTED_LAUNCH(kfn, dim3(nch), dim3(TRK_THREADS), smem, s, a);
+  } else {
+    auto kfn = track_kernel<false>;
+    SGX_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SGX_COUNTED_LAUNCH(kfn, dim3(nch), dim3(TRK_THREADS), smem, s, a);
+  }
+  SGX_CUDA(cudaGetLastError());
+  if (out_on_host) SGX_CUDA(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, s));
+  int* h_status = (int*)malloc(sizeof(int) * nch);
+  SGX_CUDA(cudaMemcpyAsync(ms_done, a.ms_done, sizeof(int) * nch, cudaMemcpyDeviceToHost, s));
+  SGX_CUDA(cudaMemcpyAsync(h_status, a.status, sizeof(int) * nch, cudaMemcpyDeviceToHost, s));
+  SGX_CUDA(cudaStreamSynchronize(s));
+  int rc = SGX_OK;
+  for (int i = 0; i < nch; ++i)
+    if (h_status[i] != SGX_OK && rc == SGX_OK) rc = h_status[i];
+  free(h_status);
+  if (rc == SGX_ERR_SHORT) return fail(rc, "sgx_track", "Not able to read the specified number of samples for tracking");
+  if (rc != SGX_OK) return fail(rc, "sgx_track", "loop state left the supported range");
+  return SGX_OK;
+}

@@ -1,0 +1,138 @@
+"""GPU parity of the tracking path (sgx_track through the package API) against the reference's
+golden outputs and against the oracle on fresh seeds.  Run on the B200 box: pytest -m gpu."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.cases import CASES, N, case_settings
+from tests.gpu_util import channels_from_gold, compare_tracking, gold
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def native():
+    from softgnss_python_b200 import _native
+    L = _native.lib()
+    L.require_device()
+    return _native
+
+
+def _fields(res):
+    from softgnss_python_b200.tracking import FIELDS
+    return {f: np.stack([np.asarray(x, dtype=np.float64) for x in res[f]]) for f in FIELDS}
+
+
+def test_library_loaded_and_abi(native):
+    assert native.lib().dll.sgx_abi_version() == 1
+    assert native.lib().dll.sgx_device_count() >= 1
+
+
+def test_synth_device_bit_identical(native, recordings):
+    from softgnss_python_b200 import synth
+    spec, data = recordings["trk_skip"]
+    specs, bits = native.make_synth_specs([spec])
+    for start, n in ((0, 2 * N + 3), (777, 65536), (5 * N - 1, 4097)):
+        out = np.zeros((1, n + 16), dtype=np.int8)
+        native.lib().synth(out, out.strides[0], n, start, specs, bits, synth.cos_lut(), native.ca_chips_int8())
+        assert np.array_equal(out[0, :n], data[start:start + n])
+        assert not out[0, n:].any()
+
+
+@pytest.mark.parametrize("stage", ["bulk", "cpasync"])
+@pytest.mark.parametrize("name", ["trk_small", "trk_skip"])
+def test_tracking_matches_reference_golden(native, recordings, name, stage, monkeypatch):
+    from softgnss_python_b200.tracking import tracking
+    monkeypatch.setenv("SGX_TRK_STAGE", stage)
+    g = gold(name)
+    _, data = recordings[name]
+    s = case_settings(CASES[name])
+    ch = channels_from_gold(g)
+    res, ch2 = tracking(data, ch, s)
+    assert ch2 is ch
+    assert res.PRN.tolist() == g["trk_PRN"].tolist()
+    assert res.dtype.names == ("status",) + tuple(native.TRACK_FIELDS) + ("PRN",)
+    assert res.dtype["status"] == np.dtype("S1") and res.dtype["I_P"] == np.dtype("O")
+    got = _fields(res)
+    ref = {f: g["trk_" + f] for f in native.TRACK_FIELDS}
+    compare_tracking(got, ref, name)
+
+
+def test_tracking_class_surface_and_file_object(native, recordings, tmp_path):
+    """TrackingResult(acqResult).track(fid) with an open file, as initialize.py:502-507 calls it."""
+    from softgnss_python_b200.tracking import TrackingResult
+    name = "trk_skip"
+    g = gold(name)
+    _, data = recordings[name]
+    s = case_settings(CASES[name])
+
+    class Acq(object):
+        channels = channels_from_gold(g)
+        settings = s
+    p = tmp_path / "rec.bin"
+    data.tofile(str(p))
+    t = TrackingResult(Acq())
+    with open(str(p), "rb") as fid:
+        assert t.track(fid) is None
+    assert isinstance(t.results, np.recarray) and len(t.results) == 2      # idle channel omitted
+    assert np.array_equal(np.asarray(t.results[0].absoluteSample), g["trk_absoluteSample"][0])
+
+
+def test_short_recording_returns_none(native, recordings, capsys):
+    from softgnss_python_b200.tracking import tracking
+    g = gold("trk_skip")
+    _, data = recordings["trk_skip"]
+    s = case_settings(CASES["trk_skip"])
+    res, _ = tracking(data[:60 * N], channels_from_gold(g), s)
+    assert res is None
+    assert "Not able to read the specified number of samples" in capsys.readouterr().out
+
+
+def test_fresh_seed_against_oracle(native):
+    """Inputs the golden set has never seen: oracle and CUDA path on the same bytes."""
+    from oracle import gnss_oracle as orc
+    from softgnss_python_b200 import synth
+    from softgnss_python_b200.settings import Settings
+    from softgnss_python_b200.tracking import tracking
+    sats = synth.default_constellation(seed=99, n_sats=4, cn0=48.0)
+    spec = synth.RecordingSpec(sats, seed=99)
+    ms = 60
+    data = synth.generate_cpu(spec, (ms + 3) * N)
+    s = Settings(numberOfChannels=4, msToProcess=float(ms))
+    prn = np.array([x.prn for x in sats], dtype=np.int64)
+    freq = np.array([spec.true_carr_freq(i) - 30.0 for i in range(4)])
+    cph = np.array([(x.code_phase + 1) % N for x in sats], dtype=np.float64)
+    ch = np.rec.fromarrays([prn, freq, cph, ['T'] * 4], names="PRN,acquiredFreq,codePhase,status")
+    recs = orc.track(data, dict(PRN=prn, acquiredFreq=freq, codePhase=cph, status=['T'] * 4), s)
+    res, _ = tracking(data, ch, s)
+    got = _fields(res)
+    ref = {f: np.stack([r[2][f] for r in recs]) for f in native.TRACK_FIELDS}
+    compare_tracking(got, ref, "fresh")
+
+
+def test_batch_device_resident_equals_single(native, recordings):
+    """R recordings resident in HBM, results written to HBM: each must equal its single-recording run
+    (the shard-invariance property multi-GPU runs rely on)."""
+    import torch
+    from softgnss_python_b200.tracking import track_batch
+    g = gold("trk_small")
+    _, data = recordings["trk_small"]
+    s = case_settings(CASES["trk_small"])
+    s.msToProcess = 100.0
+    ch = channels_from_gold(g)
+    n = data.size
+    stride = (n + 15) // 16 * 16 + 64
+    host = np.zeros((3, stride), dtype=np.int8)
+    host[0, :n] = data
+    host[1, :n - N] = data[N:]          # the same signal one code period later
+    host[2, :n] = data
+    dev = torch.from_numpy(host).cuda()
+    out = torch.zeros((3, 4, 13, 100), dtype=torch.float64, device="cuda")
+    rc, _, done = track_batch(dev, [n, n - N, n], [ch, ch, ch], s, out=out,
+                              stream=torch.cuda.current_stream().cuda_stream)
+    assert rc == 0 and (done == 100).all()
+    o = out.cpu().numpy()
+    assert np.array_equal(o[0], o[2])
+    rc1, o1, _ = track_batch(host[:1, :n].copy(), [n], [ch], s)
+    assert rc1 == 0 and np.array_equal(o1[0], o[0])
