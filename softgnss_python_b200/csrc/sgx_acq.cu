@@ -1,0 +1,503 @@
+// Acquisition hot path: parallel code-phase search + fine-frequency search on the device.
+//
+// Replaces reference acquisition.py:49-204:
+//   A4  block views / DC removal                        acquisition.py:55-65
+//   A5  conj(FFT(C/A code table row))                   acquisition.py:95     -> cached per settings
+//   A6  Doppler grid + carrier wipe-off (sin + j cos)   acquisition.py:99-117
+//   A7  |IFFT(FFT(x) * codeSpec)|^2                     acquisition.py:115-126
+//   A8  keep the block with the larger maximum          acquisition.py:129-133
+//   A9  peak, +-1 chip exclusion, peak ratio, decision  acquisition.py:139-166
+//   A10 code-stripped zero-padded FFT, slice arg-max    acquisition.py:170-193
+//
+// Restructuring (results unchanged): the wiped-off spectrum FFT(x * carrier_k) does not depend on
+// the PRN, so it is computed once per (recording, block, bin) -- 58 forward FFTs instead of 1856 --
+// and the hot loop is   spectrum x code spectrum -> inverse FFT -> |.|^2 -> arg-max   with the
+// multiply fused into the first pass' load and the magnitude/arg-max fused into the last pass'
+// epilogue, so correlation rows are never written.  The second peak needs the winning row again:
+// it is recomputed for the one winning (bin, block) per PRN with a masked arg-max epilogue
+// (32 extra inverse FFTs, +1.7 %).  All transforms are float32.
+#include "sgx_fft.cuh"
+
+namespace sgx {
+using fft::cpx;
+
+// ------------------------------------------------------------------------------ prologues
+struct ProNco {  // A6: int8 sample x (sin + j cos) of bin k; batch = (rec*blocks + blk)*nbins + bin
+  const int8_t* sig;
+  long long rec_stride;
+  const double* cps;  // [nbins] carrier cycles per sample = f_k / fs
+  int nbins, blocks, n;
+  __device__ __forceinline__ cpx load(int batch, int i) const {
+    const int bin = batch % nbins;
+    const int rb = batch / nbins;
+    const int blk = rb % blocks, rec = rb / blocks;
+    const float x = (float)sig[(long long)rec * rec_stride + (long long)blk * n + i];
+    double ph = (double)i * cps[bin];
+    ph -= rint(ph);
+    float s, c;
+    sincospif(2.0f * (float)ph, &s, &c);
+    return make_float2(x * s, x * c);
+  }
+};
+
+struct ProCode {  // A5: row of the sampled C/A table (tiled over coherent ms), real input
+  const int8_t* table;  // [32][n1]
+  int n1;
+  __device__ __forceinline__ cpx load(int prn, int i) const {
+    return make_float2((float)table[(long long)prn * n1 + (i % n1)], 0.f);
+  }
+};
+
+struct SearchDims {
+  int nprn, nbins, blocks, prn_first;
+};
+
+struct ProMul {  // A7 first half: spectrum x conj(code spectrum); batch -> item = item0 + batch
+  const cpx* spec;   // [rec][blk][bin][n]
+  const cpx* codeF;  // [32][n]
+  SearchDims d;
+  int n;
+  long long item0;
+  __device__ __forceinline__ cpx load(int batch, int i) const {
+    long long item = item0 + batch;
+    const int blk = (int)(item % d.blocks); item /= d.blocks;
+    const int bin = (int)(item % d.nbins); item /= d.nbins;
+    const int prn = (int)(item % d.nprn);
+    const int rec = (int)(item / d.nprn);
+    const cpx a = spec[(((long long)rec * d.blocks + blk) * d.nbins + bin) * n + i];
+    const cpx b = codeF[(long long)(d.prn_first + prn) * n + i];
+    return fft::cmulf(a, b);
+  }
+};
+
+struct PeakSel {  // per (rec, prn): result of A8/A9 first half
+  int bin, blk, codePhase;
+  float peak;
+};
+
+struct ProMulSel {  // same product for the winning (bin, block) of PRN item (rec*nprn + prn)
+  const cpx* spec;
+  const cpx* codeF;
+  const PeakSel* sel;
+  SearchDims d;
+  int n;
+  __device__ __forceinline__ cpx load(int batch, int i) const {
+    const PeakSel s = sel[batch];
+    const int prn = batch % d.nprn, rec = batch / d.nprn;
+    const cpx a = spec[(((long long)rec * d.blocks + s.blk) * d.nbins + s.bin) * n + i];
+    const cpx b = codeF[(long long)(d.prn_first + prn) * n + i];
+    return fft::cmulf(a, b);
+  }
+};
+
+struct FineItem {
+  int rec, prn, codePhase, pad;
+};
+
+struct ProFine {  // A10: (x - mean) * code, zero padded
+  const int8_t* sig;
+  long long rec_stride;
+  const long long* sums;  // [rec] integer sum of the whole recording
+  long long n_samples;
+  const int8_t* chips;        // [32][1023]
+  const unsigned short* idx;  // [nvalid]
+  const FineItem* items;
+  int nvalid;
+  __device__ __forceinline__ cpx load(int batch, int i) const {
+    if (i >= nvalid) return make_float2(0.f, 0.f);
+    const FineItem it = items[batch];
+    const float mean = (float)((double)sums[it.rec] / (double)n_samples);
+    const float x = (float)sig[(long long)it.rec * rec_stride + it.codePhase + i] - mean;
+    return make_float2(x * (float)chips[it.prn * 1023 + idx[i]], 0.f);
+  }
+};
+
+// ------------------------------------------------------------------------------ epilogues
+struct EpiPeak {  // |.|^2 and arg-max of the whole row; one key per (item, tile)
+  unsigned long long* partial;
+  int ntiles;
+  long long item0;
+  unsigned long long best;
+  __device__ __forceinline__ void begin() { best = 0ull; }
+  __device__ __forceinline__ void put(int, int i, cpx v) {
+    const float mag = fmaf(v.x, v.x, v.y * v.y);
+    const unsigned long long k = fft::peak_key(mag, (unsigned)i);
+    best = k > best ? k : best;
+  }
+  __device__ __forceinline__ void finish(int batch, int tile) {
+    const unsigned long long k = fft::block_max_key(best);
+    if (threadIdx.x == 0) partial[(item0 + batch) * ntiles + tile] = k;
+  }
+};
+
+// acquisition.py:147-159: is code phase i a candidate for the second peak?
+__device__ __forceinline__ bool second_peak_candidate(int i, int c, int w, int n) {
+  const int lo = c - w, hi = c + w;
+  if (lo <= 0) return i >= hi && i <= n + lo;  // (index n itself, the reference's IndexError, cannot occur)
+  if (hi >= n - 1) {
+    const int a = hi - n, b = lo - 1;           // a >= -1; -1 is numpy's "last element"
+    return (i >= a && i <= b) || (a < 0 && i == n + a);
+  }
+  return i <= lo || i >= hi;
+}
+
+struct EpiSecond {  // arg-max over the candidates only
+  unsigned long long* partial;
+  const PeakSel* sel;
+  int ntiles, chip, n;
+  unsigned long long best;
+  __device__ __forceinline__ void begin() { best = 0ull; }
+  __device__ __forceinline__ void put(int batch, int i, cpx v) {
+    if (!second_peak_candidate(i, sel[batch].codePhase, chip, n)) return;
+    const float mag = fmaf(v.x, v.x, v.y * v.y);
+    const unsigned long long k = fft::peak_key(mag, (unsigned)i);
+    best = k > best ? k : best;
+  }
+  __device__ __forceinline__ void finish(int batch, int tile) {
+    const unsigned long long k = fft::block_max_key(best);
+    if (threadIdx.x == 0) partial[(long long)batch * ntiles + tile] = k;
+  }
+};
+
+struct EpiFine {  // acquisition.py:186-187: arg-max over fftxc[4 : uniq-5], index relative to the slice
+  unsigned long long* partial;
+  int ntiles, lo, hi;  // candidates lo <= k < hi
+  unsigned long long best;
+  __device__ __forceinline__ void begin() { best = 0ull; }
+  __device__ __forceinline__ void put(int, int i, cpx v) {
+    if (i < lo || i >= hi) return;
+    const float mag = fmaf(v.x, v.x, v.y * v.y);
+    const unsigned long long k = fft::peak_key(mag, (unsigned)(i - lo));
+    best = k > best ? k : best;
+  }
+  __device__ __forceinline__ void finish(int batch, int tile) {
+    const unsigned long long k = fft::block_max_key(best);
+    if (threadIdx.x == 0) partial[(long long)batch * ntiles + tile] = k;
+  }
+};
+
+// ------------------------------------------------------------------------------ small kernels
+__global__ void sum_kernel(const int8_t* sig, long long rec_stride, long long n, unsigned long long* sums) {
+  const int rec = blockIdx.y;
+  const int8_t* p = sig + (long long)rec * rec_stride;
+  long long acc = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    acc += p[i];
+  int lo = (int)acc;  // per-thread sums are tiny
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) lo += __shfl_xor_sync(0xffffffffu, lo, m);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&sums[rec], (unsigned long long)(long long)lo);
+}
+
+// A8 + first half of A9 for one (rec, prn): block choice per bin, global peak, bin and code phase.
+__global__ void select_kernel(const unsigned long long* partial, int ntiles, SearchDims d, PeakSel* sel) {
+  const int item = blockIdx.x;  // rec * nprn + prn
+  __shared__ unsigned long long row[512];  // [bin][blk], nbins*blocks <= 512
+  const int rows = d.nbins * d.blocks;
+  for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+    const unsigned long long* p = partial + ((long long)item * rows + r) * ntiles;
+    unsigned long long best = 0ull;
+    for (int t = 0; t < ntiles; ++t) best = p[t] > best ? p[t] : best;
+    row[r] = best;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float peak = -1.f;
+    int fbin = 0, fblk = 0;
+    unsigned cp = 0xFFFFFFFFu;
+    for (int bin = 0; bin < d.nbins; ++bin) {
+      unsigned long long best = row[bin * d.blocks];
+      int bb = 0;
+      for (int b = 1; b < d.blocks; ++b) {  // acquisition.py:129-133: an earlier block survives only if strictly larger
+        const unsigned long long k = row[bin * d.blocks + b];
+        if (!(fft::key_value(best) > fft::key_value(k))) { best = k; bb = b; }
+      }
+      const float v = fft::key_value(best);
+      const unsigned idx = fft::key_index(best);
+      if (v > peak) { peak = v; fbin = bin; fblk = bb; cp = idx; }   // results.max(1).argmax(): first bin
+      else if (v == peak && idx < cp) cp = idx;                       // results.max(0).argmax(): first column
+    }
+    PeakSel s;
+    s.bin = fbin; s.blk = fblk; s.codePhase = (int)cp; s.peak = peak;
+    sel[item] = s;
+  }
+}
+
+__global__ void metric_kernel(const unsigned long long* partial2, int ntiles, const PeakSel* sel, int nitems,
+                              double* metric, int* codePhase, int* frqBin) {
+  const int item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= nitems) return;
+  unsigned long long best = 0ull;
+  for (int t = 0; t < ntiles; ++t) {
+    const unsigned long long k = partial2[(long long)item * ntiles + t];
+    best = k > best ? k : best;
+  }
+  metric[item] = (double)sel[item].peak / (double)fft::key_value(best);   // acquisition.py:164
+  codePhase[item] = sel[item].codePhase;
+  frqBin[item] = sel[item].bin;
+}
+
+__global__ void fine_reduce_kernel(const unsigned long long* partial, int ntiles, int nitems, int* index) {
+  const int item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= nitems) return;
+  unsigned long long best = 0ull;
+  for (int t = 0; t < ntiles; ++t) {
+    const unsigned long long k = partial[(long long)item * ntiles + t];
+    best = k > best ? k : best;
+  }
+  index[item] = (int)fft::key_index(best);
+}
+
+// ------------------------------------------------------------------------------ host side
+template <class Pro, class Epi>
+static int launch_pass(const fft::Plan& pl, int p, bool inverse, int batch, Pro pro, Epi epi, cudaStream_t s) {
+  if (batch <= 0) return SGX_OK;
+  const fft::Pass& P = pl.pass[p];
+  if (batch > 65535) return fail(SGX_ERR_ARG, "launch_pass", "batch exceeds gridDim.y");
+  dim3 grid(P.ntiles, batch, 1);
+#define SGX_FFT_GO(INV, BIG)                                                                      \
+  {                                                                                               \
+    auto kfn = fft::fft_pass_kernel<Pro, Epi, INV, BIG>;                                          \
+    SGX_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem[p])); \
+    SGX_COUNTED_LAUNCH(kfn, grid, dim3(fft::FFT_THREADS), pl.smem[p], s, P, pro, epi);            \
+  }
+  if (inverse) { if (pl.big) SGX_FFT_GO(true, true) else SGX_FFT_GO(true, false) }
+  else         { if (pl.big) SGX_FFT_GO(false, true) else SGX_FFT_GO(false, false) }
+#undef SGX_FFT_GO
+  SGX_CUDA(cudaGetLastError());
+  return SGX_OK;
+}
+
+// full transform of `batch` rows: first pass reads through `pro`, last pass writes through `epi`,
+// passes in between ping-pong through w0/w1 (each batch*N complex)
+template <class Pro, class Epi>
+static int run_fft(const fft::Plan& pl, bool inverse, int batch, Pro pro, Epi epi, cpx* w0, cpx* w1, cudaStream_t s) {
+  const long long n = pl.N;
+  if (pl.npass == 1) return launch_pass(pl, 0, inverse, batch, pro, epi, s);
+  cpx* cur = w0;
+  cpx* oth = w1;
+  int rc = launch_pass(pl, 0, inverse, batch, pro, fft::StoreCpx{cur, n, 1.f, 0}, s);
+  if (rc) return rc;
+  for (int p = 1; p + 1 < pl.npass; ++p) {
+    rc = launch_pass(pl, p, inverse, batch, fft::LoadCpx{cur, n}, fft::StoreCpx{oth, n, 1.f, 0}, s);
+    if (rc) return rc;
+    cpx* t = cur; cur = oth; oth = t;
+  }
+  return launch_pass(pl, pl.npass - 1, inverse, batch, fft::LoadCpx{cur, n}, epi, s);
+}
+
+struct AcqPlan {
+  bool valid = false;
+  sgx_settings st;
+  unsigned long long table_hash = 0;
+  int n = 0, n1 = 0, nfft = 0, nvalid = 0;
+  fft::Plan fwd, inv, fine;
+  DevBuf codeF, table, chips, fidx, cps, sig, spec, work0, work1, partial, partial2, sel, sums, metric, cph, fbin,
+      fitems, fpartial, findex;
+};
+static AcqPlan g_acq;
+
+static unsigned long long fnv(const void* p, size_t n, unsigned long long h = 1469598103934665603ULL) {
+  const unsigned char* b = (const unsigned char*)p;
+  for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ULL; }
+  return h;
+}
+
+static int ensure_plan(const sgx_settings* st, const int8_t* ca_table, const int8_t* ca_chips,
+                       const uint16_t* fine_idx, cudaStream_t s) {
+  AcqPlan& a = g_acq;
+  const int n1 = st->samplesPerCode;
+  unsigned long long h = fnv(ca_table, (size_t)32 * n1);
+  h = fnv(fine_idx, sizeof(uint16_t) * (size_t)st->fineMs * n1, h);
+  if (a.valid && memcmp(&a.st, st, sizeof(*st)) == 0 && a.table_hash == h) return SGX_OK;
+  a.valid = false;
+  a.st = *st;
+  a.table_hash = h;
+  a.n1 = n1;
+  a.n = n1 * st->acqCoherentMs;
+  a.nvalid = st->fineMs * n1;
+  int lg = 0;
+  while ((1LL << lg) < a.nvalid) ++lg;   // 2^ceil(log2(len)), acquisition.py:179
+  a.nfft = 8 << lg;
+  int rc;
+  if ((rc = fft::build_plan(a.fwd, a.n, false, s))) return rc;
+  if ((rc = fft::build_plan(a.inv, a.n, true, s))) return rc;
+  if ((rc = fft::build_plan(a.fine, a.nfft, false, s))) return rc;
+  if (a.table.reserve((size_t)32 * n1) || a.chips.reserve(32 * 1023) || a.fidx.reserve(sizeof(uint16_t) * a.nvalid) ||
+      a.codeF.reserve(sizeof(cpx) * (size_t)32 * a.n) || a.cps.reserve(sizeof(double) * st->numFrqBins) ||
+      a.work0.reserve(sizeof(cpx) * (size_t)32 * a.n) || a.work1.reserve(sizeof(cpx) * (size_t)32 * a.n))
+    return fail(SGX_ERR_CUDA, "cudaMalloc", "acquisition plan");
+  SGX_CUDA(cudaMemcpyAsync(a.table.p, ca_table, (size_t)32 * n1, cudaMemcpyHostToDevice, s));
+  SGX_CUDA(cudaMemcpyAsync(a.chips.p, ca_chips, 32 * 1023, cudaMemcpyHostToDevice, s));
+  SGX_CUDA(cudaMemcpyAsync(a.fidx.p, fine_idx, sizeof(uint16_t) * a.nvalid, cudaMemcpyHostToDevice, s));
+  // Doppler grid (acquisition.py:99-101) in float64 on the host
+  double* cps = (double*)malloc(sizeof(double) * st->numFrqBins);
+  for (int k = 0; k < st->numFrqBins; ++k) {
+    const double f = st->IF - st->acqSearchBand / 2 * 1000 + st->acqDopplerStep * k;
+    cps[k] = f / st->samplingFreq;
+  }
+  SGX_CUDA(cudaMemcpyAsync(a.cps.p, cps, sizeof(double) * st->numFrqBins, cudaMemcpyHostToDevice, s));
+  SGX_CUDA(cudaStreamSynchronize(s));
+  free(cps);
+  // A5: conj(FFT(code)) / n for all 32 PRNs
+  rc = run_fft(a.fwd, false, 32, ProCode{a.table.as<int8_t>(), n1},
+               fft::StoreCpx{a.codeF.as<cpx>(), (long long)a.n, 1.0f / (float)a.n, 1}, a.work0.as<cpx>(),
+               a.work1.as<cpx>(), s);
+  if (rc) return rc;
+  a.valid = true;
+  return SGX_OK;
+}
+
+}  // namespace sgx
+
+using namespace sgx;
+
+extern "C" int sgx_acquire(const int8_t* sig, int64_t rec_stride, int64_t n_samples, int32_t n_recordings,
+                           const sgx_settings* st, const int8_t* ca_table, const int8_t* ca_chips,
+                           const uint16_t* fine_idx, int32_t prn_first, int32_t prn_count, double* carrFreq,
+                           double* codePhase, double* peakMetric, int32_t* frqBin, int32_t* finePeakIndex,
+                           void* cuda_stream) {
+  if (sgx_device_count() <= 0) return fail(SGX_ERR_NODEV, "sgx_acquire", "no CUDA device");
+  if (!sig || !st || !ca_table || !ca_chips || !fine_idx || !carrFreq || !codePhase || !peakMetric ||
+      n_recordings <= 0 || prn_first < 0 || prn_count <= 0 || prn_first + prn_count > SGX_NUM_PRN)
+    return fail(SGX_ERR_ARG, "sgx_acquire", "null pointer or PRN shard outside 0..32");
+  const int n1 = st->samplesPerCode, blocks = st->acqNonCoherentBlocks, nbins = st->numFrqBins;
+  const long long n = (long long)n1 * st->acqCoherentMs;
+  if (n_samples < n * blocks || n_samples < (long long)(st->fineMs + 1) * n1 || nbins * blocks > 512 || nbins <= 0)
+    return fail(SGX_ERR_ARG, "sgx_acquire", "longSignal too short (needs blocks and fineMs+1 code periods) or too many bins");
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  int rc = ensure_plan(st, ca_table, ca_chips, fine_idx, s);
+  if (rc) return rc;
+  AcqPlan& a = g_acq;
+  const int R = n_recordings;
+
+  const int8_t* d_sig = sig;
+  long long stride = rec_stride;
+  if (!is_device_ptr(sig)) {
+    stride = n_samples;
+    if (a.sig.reserve((size_t)stride * R)) return fail(SGX_ERR_CUDA, "cudaMalloc", "signal");
+    for (int r = 0; r < R; ++r)
+      SGX_CUDA(cudaMemcpyAsync(a.sig.as<int8_t>() + (size_t)r * stride, sig + (size_t)r * rec_stride, (size_t)n_samples,
+                               cudaMemcpyHostToDevice, s));
+    d_sig = a.sig.as<int8_t>();
+  }
+
+  SearchDims d;
+  d.nprn = prn_count; d.nbins = nbins; d.blocks = blocks; d.prn_first = prn_first;
+  const int nspec = R * blocks * nbins;
+  const long long nitems = (long long)R * prn_count * nbins * blocks;
+  const int npr = R * prn_count;
+  const int nt_last = a.inv.pass[a.inv.npass - 1].ntiles;
+  // scratch
+  long long chunk_mb = 64;
+  if (const char* e = getenv("SGX_ACQ_CHUNK_MB")) chunk_mb = atoll(e) > 0 ? atoll(e) : chunk_mb;
+  long long chunk = (chunk_mb << 20) / ((long long)sizeof(cpx) * n);
+  if (chunk < 1) chunk = 1;
+  if (chunk > 32768) chunk = 32768;
+  long long wneed = chunk > nspec ? chunk : nspec;
+  if (wneed < npr) wneed = npr;
+  if (wneed < 32) wneed = 32;
+  const bool two_bufs = a.inv.npass > 2 || a.fwd.npass > 2;
+  if (a.spec.reserve(sizeof(cpx) * (size_t)nspec * n) || a.work0.reserve(sizeof(cpx) * (size_t)wneed * n) ||
+      (two_bufs && a.work1.reserve(sizeof(cpx) * (size_t)wneed * n)) ||
+      a.partial.reserve(sizeof(unsigned long long) * (size_t)nitems * nt_last) ||
+      a.partial2.reserve(sizeof(unsigned long long) * (size_t)npr * nt_last) || a.sel.reserve(sizeof(PeakSel) * npr) ||
+      a.sums.reserve(sizeof(unsigned long long) * R) || a.metric.reserve(sizeof(double) * npr) ||
+      a.cph.reserve(sizeof(int) * npr) || a.fbin.reserve(sizeof(int) * npr))
+    return fail(SGX_ERR_CUDA, "cudaMalloc", "acquisition scratch");
+
+  // ---- A4: integer sum of the whole longSignal (for the DC removal of A10) ---------------------
+  SGX_CUDA(cudaMemsetAsync(a.sums.p, 0, sizeof(unsigned long long) * R, s));
+  SGX_COUNTED_LAUNCH(sum_kernel, dim3(64, R), dim3(256), 0, s, d_sig, stride, (long long)n_samples,
+                     a.sums.as<unsigned long long>());
+  // ---- A6 + forward half of A7: one spectrum per (rec, block, bin) -----------------------------
+  if (nspec > 32768 || npr > 32768)
+    return fail(SGX_ERR_ARG, "sgx_acquire", "too many recordings in one call (split the batch)");
+  rc = run_fft(a.fwd, false, nspec, ProNco{d_sig, stride, a.cps.as<double>(), nbins, blocks, (int)n},
+               fft::StoreCpx{a.spec.as<cpx>(), n, 1.f, 0}, a.work0.as<cpx>(), a.work1.as<cpx>(), s);
+  if (rc) return rc;
+  // ---- A7: spectrum x code -> IFFT -> |.|^2 -> per-row arg-max, in L2-sized chunks -------------
+  for (long long i0 = 0; i0 < nitems; i0 += chunk) {
+    const int cnt = (int)((nitems - i0) < chunk ? (nitems - i0) : chunk);
+    EpiPeak ep;
+    ep.partial = a.partial.as<unsigned long long>(); ep.ntiles = nt_last; ep.item0 = i0; ep.best = 0;
+    rc = run_fft(a.inv, true, cnt, ProMul{a.spec.as<cpx>(), a.codeF.as<cpx>(), d, (int)n, i0}, ep, a.work0.as<cpx>(),
+                 a.work1.as<cpx>(), s);
+    if (rc) return rc;
+  }
+  // ---- A8 + A9 -------------------------------------------------------------------------------
+  SGX_COUNTED_LAUNCH(select_kernel, dim3(npr), dim3(128), 0, s, a.partial.as<unsigned long long>(), nt_last, d,
+                     a.sel.as<PeakSel>());
+  {
+    EpiSecond es;
+    es.partial = a.partial2.as<unsigned long long>(); es.sel = a.sel.as<PeakSel>(); es.ntiles = nt_last;
+    es.chip = st->samplesPerCodeChip; es.n = (int)n; es.best = 0;
+    rc = run_fft(a.inv, true, npr, ProMulSel{a.spec.as<cpx>(), a.codeF.as<cpx>(), a.sel.as<PeakSel>(), d, (int)n}, es,
+                 a.work0.as<cpx>(), a.work1.as<cpx>(), s);
+    if (rc) return rc;
+  }
+  SGX_COUNTED_LAUNCH(metric_kernel, dim3((npr + 127) / 128), dim3(128), 0, s, a.partial2.as<unsigned long long>(),
+                     nt_last, a.sel.as<PeakSel>(), npr, a.metric.as<double>(), a.cph.as<int>(), a.fbin.as<int>());
+  SGX_CUDA(cudaGetLastError());
+  int* h_cph = (int*)malloc(sizeof(int) * npr * 2);
+  int* h_bin = h_cph + npr;
+  SGX_CUDA(cudaMemcpyAsync(peakMetric, a.metric.p, sizeof(double) * npr, cudaMemcpyDeviceToHost, s));
+  SGX_CUDA(cudaMemcpyAsync(h_cph, a.cph.p, sizeof(int) * npr, cudaMemcpyDeviceToHost, s));
+  SGX_CUDA(cudaMemcpyAsync(h_bin, a.fbin.p, sizeof(int) * npr, cudaMemcpyDeviceToHost, s));
+  SGX_CUDA(cudaStreamSynchronize(s));
+  // ---- decision (acquisition.py:166) and A10 for the detected PRNs ----------------------------
+  FineItem* items = (FineItem*)malloc(sizeof(FineItem) * npr);
+  int* slot = (int*)malloc(sizeof(int) * npr);
+  int nf = 0;
+  for (int i = 0; i < npr; ++i) {
+    carrFreq[i] = 0.0;
+    codePhase[i] = 0.0;
+    if (frqBin) frqBin[i] = h_bin[i];
+    if (finePeakIndex) finePeakIndex[i] = -1;
+    if (peakMetric[i] > st->acqThreshold) {
+      items[nf].rec = i / prn_count;
+      items[nf].prn = prn_first + i % prn_count;
+      items[nf].codePhase = h_cph[i];
+      items[nf].pad = 0;
+      slot[nf++] = i;
+      codePhase[i] = (double)h_cph[i];                                   // :193
+    }
+  }
+  if (nf > 0) {
+    const int nt_f = a.fine.pass[a.fine.npass - 1].ntiles;
+    const int uniq = a.nfft / 2 + 1;                                      // ceil((nfft+1)/2), :184
+    int fchunk = (int)((256LL << 20) / ((long long)sizeof(cpx) * a.nfft));
+    if (fchunk < 1) fchunk = 1;
+    if (a.fitems.reserve(sizeof(FineItem) * nf) || a.fpartial.reserve(sizeof(unsigned long long) * (size_t)nf * nt_f) ||
+        a.findex.reserve(sizeof(int) * nf) || a.work0.reserve(sizeof(cpx) * (size_t)fchunk * a.nfft) ||
+        a.work1.reserve(sizeof(cpx) * (size_t)fchunk * a.nfft))
+      return fail(SGX_ERR_CUDA, "cudaMalloc", "fine search scratch");
+    SGX_CUDA(cudaMemcpyAsync(a.fitems.p, items, sizeof(FineItem) * nf, cudaMemcpyHostToDevice, s));
+    for (int f0 = 0; f0 < nf; f0 += fchunk) {
+      const int cnt = nf - f0 < fchunk ? nf - f0 : fchunk;
+      EpiFine ef;
+      ef.partial = a.fpartial.as<unsigned long long>() + (size_t)f0 * nt_f; ef.ntiles = nt_f; ef.lo = 4;
+      ef.hi = uniq - 5; ef.best = 0;
+      ProFine pf{d_sig, stride, (const long long*)a.sums.p, (long long)n_samples, a.chips.as<int8_t>(),
+                 a.fidx.as<unsigned short>(), a.fitems.as<FineItem>() + f0, a.nvalid};
+      rc = run_fft(a.fine, false, cnt, pf, ef, a.work0.as<cpx>(), a.work1.as<cpx>(), s);
+      if (rc) return rc;
+    }
+    SGX_COUNTED_LAUNCH(fine_reduce_kernel, dim3((nf + 127) / 128), dim3(128), 0, s, a.fpartial.as<unsigned long long>(),
+                       nt_f, nf, a.findex.as<int>());
+    SGX_CUDA(cudaGetLastError());
+    int* h_idx = (int*)malloc(sizeof(int) * nf);
+    SGX_CUDA(cudaMemcpyAsync(h_idx, a.findex.p, sizeof(int) * nf, cudaMemcpyDeviceToHost, s));
+    SGX_CUDA(cudaStreamSynchronize(s));
+    for (int f = 0; f < nf; ++f) {
+      // fftFreqBins[fftMaxIndex] = arange(uniq) * fs / nfft evaluated at the slice-relative index (:189-191)
+      carrFreq[slot[f]] = (double)h_idx[f] * st->samplingFreq / (double)a.nfft;
+      if (finePeakIndex) finePeakIndex[slot[f]] = h_idx[f];
+    }
+    free(h_idx);
+  }
+  free(items);
+  free(slot);
+  free(h_cph);
+  return SGX_OK;
+}

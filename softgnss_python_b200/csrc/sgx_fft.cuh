@@ -1,0 +1,388 @@
+// Mixed-radix FFT engine for the acquisition path (sizes such as 38192 = 16*7*11*31 and 2^22).
+//
+// A transform of length N is a short sequence of "passes" (Stockham autosort, decimation in time).
+// Pass p has a composite radix R (<= 512) and Ls = product of the earlier radices, m = N / R:
+//
+//     for j in [0, m):  k = j mod Ls
+//        y[(j-k)*R + k + u*Ls] = sum_t  x[j + t*m] * w_{Ls*R}^{t*k} * w_R^{t*u}        u in [0, R)
+//
+// One CTA owns T consecutive j ("columns"): it gathers the T x R inputs (rows of T contiguous
+// elements -> coalesced), applies the inter-pass twiddles, runs the R-point sub-FFT of all T
+// columns in shared memory (again Stockham, radices from {2,3,4,5,7,8,11,16,31}, butterflies in
+// registers with constant-bank twiddles) and scatters the result, or hands it to a fused epilogue
+// (|.|^2 + arg-max) without ever writing it.  Input prologues are fused the same way (int8 samples
+// x carrier NCO, spectrum x code spectrum, code-stripped real samples).  Output is in natural order
+// after the last pass, so bin/code-phase indices need no permutation.
+//
+// Tensor cores are deliberately not used: the 31-point stage as a dense DFT GEMM costs 4x the FMAs
+// of the symmetric butterfly below and would need a 3xTF32 split to hold the 1e-6 accuracy
+// ("Why not tcgen05").
+#pragma once
+#include "sgx_common.cuh"
+#include "sgx_fft_tables.h"
+
+namespace sgx {
+namespace fft {
+
+typedef float2 cpx;
+constexpr int MAX_SUB = 6;
+constexpr int FFT_THREADS = 128;
+
+struct Pass {
+  int N, R, Ls, m, T, nsub, ntiles, inverse;
+  int radix[MAX_SUB];
+  const cpx* twg;  // [R][Ls]: w_{Ls*R}^{t*k} (forward sign); nullptr when Ls == 1
+  const cpx* wr;   // [R]    : w_R^q           (forward sign)
+};
+
+__device__ __forceinline__ cpx cmulf(cpx a, cpx b) {
+  return make_float2(fmaf(a.x, b.x, -(a.y * b.y)), fmaf(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ cpx cadd(cpx a, cpx b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ cpx csub(cpx a, cpx b) { return make_float2(a.x - b.x, a.y - b.y); }
+template <bool INV> __device__ __forceinline__ cpx rot90(cpx a) {
+  // forward: multiply by -i ; inverse: multiply by +i
+  return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
+}
+
+// ---- butterflies (in place, natural order in and out) ---------------------------------------
+template <int N, bool INV> struct Pow2 {
+  static __device__ __forceinline__ void run(cpx* v) {
+    cpx e[N / 2], o[N / 2];
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) { e[i] = v[2 * i]; o[i] = v[2 * i + 1]; }
+    Pow2<N / 2, INV>::run(e);
+    Pow2<N / 2, INV>::run(o);
+#pragma unroll
+    for (int k = 0; k < N / 2; ++k) {
+      cpx t;
+      if (k == 0) t = o[0];
+      else if (4 * k == N) t = rot90<INV>(o[k]);
+      else {
+        const float c = COS16[k * (16 / N)], s = SIN16[k * (16 / N)];
+        t = cmulf(o[k], make_float2(c, INV ? s : -s));
+      }
+      v[k] = cadd(e[k], t);
+      v[k + N / 2] = csub(e[k], t);
+    }
+  }
+};
+template <bool INV> struct Pow2<1, INV> {
+  static __device__ __forceinline__ void run(cpx*) {}
+};
+
+template <int P, bool INV>
+__device__ __forceinline__ void dft_prime(cpx* v, const float* C, const float* S) {
+  // conjugate-pair form: a_j = x_j + x_{P-j}, b_j = x_j - x_{P-j};  X_k = C_k -/+ i S_k
+  constexpr int H = (P - 1) / 2;
+  cpx a[H], b[H];
+#pragma unroll
+  for (int j = 1; j <= H; ++j) { a[j - 1] = cadd(v[j], v[P - j]); b[j - 1] = csub(v[j], v[P - j]); }
+  const cpx x0 = v[0];
+  cpx sum = x0;
+#pragma unroll
+  for (int j = 0; j < H; ++j) sum = cadd(sum, a[j]);
+  v[0] = sum;
+#pragma unroll
+  for (int k = 1; k <= H; ++k) {
+    float cr = x0.x, ci = x0.y, sr = 0.f, si = 0.f;
+#pragma unroll
+    for (int j = 1; j <= H; ++j) {
+      const int q = (j * k) % P;
+      cr = fmaf(a[j - 1].x, C[q], cr);
+      ci = fmaf(a[j - 1].y, C[q], ci);
+      sr = fmaf(b[j - 1].x, S[q], sr);
+      si = fmaf(b[j - 1].y, S[q], si);
+    }
+    const cpx lo = make_float2(cr + si, ci - sr), hi = make_float2(cr - si, ci + sr);
+    v[k] = INV ? hi : lo;
+    v[P - k] = INV ? lo : hi;
+  }
+}
+
+template <int R, bool INV> struct Dft;
+template <bool INV> struct Dft<2, INV> { static __device__ __forceinline__ void run(cpx* v) { Pow2<2, INV>::run(v); } };
+template <bool INV> struct Dft<4, INV> { static __device__ __forceinline__ void run(cpx* v) { Pow2<4, INV>::run(v); } };
+template <bool INV> struct Dft<8, INV> { static __device__ __forceinline__ void run(cpx* v) { Pow2<8, INV>::run(v); } };
+template <bool INV> struct Dft<16, INV> { static __device__ __forceinline__ void run(cpx* v) { Pow2<16, INV>::run(v); } };
+template <bool INV> struct Dft<3, INV> { static __device__ __forceinline__ void run(cpx* v) { dft_prime<3, INV>(v, COS3, SIN3); } };
+template <bool INV> struct Dft<5, INV> { static __device__ __forceinline__ void run(cpx* v) { dft_prime<5, INV>(v, COS5, SIN5); } };
+template <bool INV> struct Dft<7, INV> { static __device__ __forceinline__ void run(cpx* v) { dft_prime<7, INV>(v, COS7, SIN7); } };
+template <bool INV> struct Dft<11, INV> { static __device__ __forceinline__ void run(cpx* v) { dft_prime<11, INV>(v, COS11, SIN11); } };
+template <bool INV> struct Dft<31, INV> { static __device__ __forceinline__ void run(cpx* v) { dft_prime<31, INV>(v, COS31, SIN31); } };
+
+// One Stockham sub-pass of radix r over the R x T tile held in shared memory (row stride TP).
+template <int r, bool INV>
+__device__ __forceinline__ void subpass(const cpx* __restrict__ in, cpx* __restrict__ out,
+                                        const cpx* __restrict__ W, int R, int ls, int T, int TP) {
+  const int mm = R / r;
+  const int total = mm * T;
+  const int wstride = R / (ls * r);
+  for (int idx = threadIdx.x; idx < total; idx += FFT_THREADS) {
+    const int jj = idx % T;
+    const int b = idx / T;
+    const int kk = b % ls;
+    cpx v[r];
+#pragma unroll
+    for (int u = 0; u < r; ++u) v[u] = in[(b + u * mm) * TP + jj];
+    if (ls > 1) {
+#pragma unroll
+      for (int u = 1; u < r; ++u) v[u] = cmulf(v[u], W[u * kk * wstride]);
+    }
+    Dft<r, INV>::run(v);
+    const int base = (b - kk) * r + kk;
+#pragma unroll
+    for (int u = 0; u < r; ++u) out[(base + u * ls) * TP + jj] = v[u];
+  }
+}
+
+template <bool INV, bool BIG>
+__device__ __forceinline__ void run_subpass(int r, const cpx* in, cpx* out, const cpx* W, int R, int ls,
+                                            int T, int TP) {
+  switch (r) {
+    case 2: subpass<2, INV>(in, out, W, R, ls, T, TP); break;
+    case 4: subpass<4, INV>(in, out, W, R, ls, T, TP); break;
+    case 8: subpass<8, INV>(in, out, W, R, ls, T, TP); break;
+    case 16: subpass<16, INV>(in, out, W, R, ls, T, TP); break;
+    default:
+      if (BIG) {
+        switch (r) {
+          case 3: subpass<3, INV>(in, out, W, R, ls, T, TP); break;
+          case 5: subpass<5, INV>(in, out, W, R, ls, T, TP); break;
+          case 7: subpass<7, INV>(in, out, W, R, ls, T, TP); break;
+          case 11: subpass<11, INV>(in, out, W, R, ls, T, TP); break;
+          case 31: subpass<31, INV>(in, out, W, R, ls, T, TP); break;
+        }
+      }
+  }
+}
+
+// Pro:  cpx load(int batch, int n)                  -- element n of transform `batch`
+// Epi:  void begin(); void put(int batch, int n, cpx v); void finish(int batch, int tile)
+template <class Pro, class Epi, bool INV, bool BIG>
+__global__ void __launch_bounds__(FFT_THREADS) fft_pass_kernel(Pass P, Pro pro, Epi epi) {
+  SGX_DYN_SMEM(smem);
+  const int R = P.R, T = P.T, TP = T + 1, m = P.m, Ls = P.Ls;
+  cpx* A = reinterpret_cast<cpx*>(smem);
+  cpx* B = A + R * TP;
+  cpx* W = B + R * TP;
+  const int tid = threadIdx.x;
+  const int tile = blockIdx.x;
+  const int batch = blockIdx.y + gridDim.y * blockIdx.z;
+  const int j0 = tile * T;
+
+  for (int q = tid; q < R; q += FFT_THREADS) {
+    cpx w = P.wr[q];
+    if (INV) w.y = -w.y;
+    W[q] = w;
+  }
+  for (int e = tid; e < R * T; e += FFT_THREADS) {
+    const int jj = e % T, t = e / T, j = j0 + jj;
+    cpx v = make_float2(0.f, 0.f);
+    if (j < m) {
+      v = pro.load(batch, j + t * m);
+      if (Ls > 1 && t > 0) {
+        cpx w = P.twg[(size_t)t * Ls + (j % Ls)];
+        if (INV) w.y = -w.y;
+        v = cmulf(v, w);
+      }
+    }
+    A[t * TP + jj] = v;
+  }
+  __syncthreads();
+  cpx* src = A;
+  cpx* dst = B;
+  int ls = 1;
+  for (int s = 0; s < P.nsub; ++s) {
+    const int r = P.radix[s];
+    run_subpass<INV, BIG>(r, src, dst, W, R, ls, T, TP);
+    ls *= r;
+    __syncthreads();
+    cpx* tmp = src; src = dst; dst = tmp;
+  }
+  epi.begin();
+  if (Ls == 1) {
+    // y[j*R + u]: contiguous in u for one column
+    for (int e = tid; e < R * T; e += FFT_THREADS) {
+      const int u = e % R, jj = e / R, j = j0 + jj;
+      if (j < m) epi.put(batch, j * R + u, src[u * TP + jj]);
+    }
+  } else {
+    for (int e = tid; e < R * T; e += FFT_THREADS) {
+      const int jj = e % T, u = e / T, j = j0 + jj;
+      if (j < m) {
+        const int k = j % Ls;
+        epi.put(batch, (j - k) * R + k + u * Ls, src[u * TP + jj]);
+      }
+    }
+  }
+  epi.finish(batch, tile);
+}
+
+// ---- generic prologues / epilogues -----------------------------------------------------------
+struct LoadCpx {  // plain complex input, transforms `stride` apart
+  const cpx* in;
+  long long stride;
+  __device__ __forceinline__ cpx load(int batch, int n) const { return in[(long long)batch * stride + n]; }
+};
+struct StoreCpx {
+  cpx* out;
+  long long stride;
+  float scale;   // applied to both parts
+  int conj;      // store the conjugate
+  __device__ __forceinline__ void begin() {}
+  __device__ __forceinline__ void put(int batch, int n, cpx v) const {
+    out[(long long)batch * stride + n] = make_float2(v.x * scale, conj ? -v.y * scale : v.y * scale);
+  }
+  __device__ __forceinline__ void finish(int, int) {}
+};
+
+// packed (value, index) key: larger value wins, then the smaller index (numpy arg-max tie rule)
+__device__ __forceinline__ unsigned long long peak_key(float v, unsigned idx) {
+  return ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
+}
+__device__ __forceinline__ float key_value(unsigned long long k) { return __uint_as_float((unsigned)(k >> 32)); }
+__device__ __forceinline__ unsigned key_index(unsigned long long k) { return 0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFu); }
+
+__device__ __forceinline__ unsigned long long block_max_key(unsigned long long key) {
+  __shared__ unsigned long long wk[FFT_THREADS / 32];
+#pragma unroll
+  for (int msk = 16; msk > 0; msk >>= 1) {
+    unsigned long long o = __shfl_xor_sync(0xffffffffu, key, msk);
+    key = o > key ? o : key;
+  }
+  if ((threadIdx.x & 31) == 0) wk[threadIdx.x >> 5] = key;
+  __syncthreads();
+  unsigned long long best = wk[0];
+#pragma unroll
+  for (int w = 1; w < FFT_THREADS / 32; ++w) best = wk[w] > best ? wk[w] : best;
+  return best;
+}
+
+// ---- twiddle / table setup --------------------------------------------------------------------
+__global__ void twiddle_kernel(cpx* out, long long count, int Ls, long long M) {
+  // Ls > 0: out[t*Ls + k] = exp(-2*pi*i * (t*k mod M) / M);   Ls == 0: out[q] = exp(-2*pi*i*q/M)
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < count;
+       e += (long long)gridDim.x * blockDim.x) {
+    long long q = e % M;
+    if (Ls > 0) {
+      long long t = e / Ls, k = e % Ls;
+      q = (t * k) % M;
+    }
+    double s, c;
+    sincospi(-2.0 * (double)q / (double)M, &s, &c);
+    out[e] = make_float2((float)c, (float)s);
+  }
+}
+
+// ---- host-side plan ---------------------------------------------------------------------------
+struct Plan {
+  int N = 0, npass = 0;
+  bool big = false;   // uses radices beyond {2,4,8,16}
+  Pass pass[4];
+  DevBuf tw[4], wr[4];
+  size_t smem[4];
+};
+
+inline bool factor_small(int n, int* radices, int& cnt) {
+  cnt = 0;
+  int twos = 0;
+  while (n % 2 == 0) { n /= 2; ++twos; }
+  while (twos >= 4) { radices[cnt++] = 16; twos -= 4; }
+  if (twos == 3) radices[cnt++] = 8;
+  if (twos == 2) radices[cnt++] = 4;
+  if (twos == 1) radices[cnt++] = 2;
+  const int odd[5] = {3, 5, 7, 11, 31};
+  for (int i = 0; i < 5; ++i)
+    while (n % odd[i] == 0) {
+      if (cnt >= 16) return false;
+      radices[cnt++] = odd[i];
+      n /= odd[i];
+    }
+  return n == 1;
+}
+
+// Split the radices of N into `np` passes with the most even products (exhaustive, tiny).
+inline bool plan_passes(int N, int maxR, int groups[4][MAX_SUB], int gcnt[4], int& np) {
+  int rad[16], cnt;
+  if (!factor_small(N, rad, cnt)) return false;
+  for (np = 1; np <= 4; ++np) {
+    long long best = -1;
+    int bestAssign[16];
+    int assign[16] = {0};
+    long long total = 1;
+    for (int i = 0; i < cnt; ++i) total *= np;
+    for (long long code = 0; code < total; ++code) {
+      long long c = code;
+      long long prod[4] = {1, 1, 1, 1};
+      int gc[4] = {0, 0, 0, 0};
+      bool ok = true;
+      for (int i = 0; i < cnt; ++i) {
+        assign[i] = (int)(c % np);
+        c /= np;
+        prod[assign[i]] *= rad[i];
+        if (++gc[assign[i]] > MAX_SUB) ok = false;
+      }
+      long long mx = 0;
+      for (int g = 0; g < np; ++g) { if (prod[g] > mx) mx = prod[g]; if (prod[g] == 1) ok = false; }
+      if (!ok || mx > maxR) continue;
+      if (best < 0 || mx < best) { best = mx; memcpy(bestAssign, assign, sizeof(assign)); }
+    }
+    if (best > 0) {
+      for (int g = 0; g < np; ++g) gcnt[g] = 0;
+      for (int i = 0; i < cnt; ++i) groups[bestAssign[i]][gcnt[bestAssign[i]]++] = rad[i];
+      return true;
+    }
+  }
+  return false;
+}
+
+inline int build_plan(Plan& pl, int N, bool inverse, cudaStream_t s, int maxR = 512) {
+  int groups[4][MAX_SUB], gcnt[4], np;
+  if (!plan_passes(N, maxR, groups, gcnt, np))
+    return fail(SGX_ERR_ARG, "fft plan", "length has a prime factor outside {2,3,5,7,11,31} or is too large");
+  pl.N = N;
+  pl.npass = np;
+  pl.big = false;
+  int Ls = 1;
+  for (int p = 0; p < np; ++p) {
+    Pass& P = pl.pass[p];
+    P.N = N;
+    P.R = 1;
+    P.nsub = gcnt[p];
+    for (int i = 0; i < gcnt[p]; ++i) {
+      // big radices first: their butterflies then run without sub-pass twiddles (ls == 1)
+      P.radix[i] = groups[p][i];
+    }
+    for (int i = 0; i < P.nsub; ++i)
+      for (int j = i + 1; j < P.nsub; ++j)
+        if (P.radix[j] > P.radix[i]) { int t = P.radix[i]; P.radix[i] = P.radix[j]; P.radix[j] = t; }
+    for (int i = 0; i < P.nsub; ++i) {
+      P.R *= P.radix[i];
+      int r = P.radix[i];
+      if (!(r == 2 || r == 4 || r == 8 || r == 16)) pl.big = true;
+    }
+    P.Ls = Ls;
+    P.m = N / P.R;
+    P.T = 16;
+    P.ntiles = (P.m + P.T - 1) / P.T;
+    P.inverse = inverse ? 1 : 0;
+    pl.smem[p] = sizeof(cpx) * ((size_t)2 * P.R * (P.T + 1) + P.R);
+    if (pl.wr[p].reserve(sizeof(cpx) * P.R)) return fail(SGX_ERR_CUDA, "cudaMalloc", "fft tables");
+    SGX_COUNTED_LAUNCH(twiddle_kernel, dim3(4), dim3(128), 0, s, pl.wr[p].as<cpx>(), (long long)P.R, 0, (long long)P.R);
+    P.wr = pl.wr[p].as<cpx>();
+    P.twg = nullptr;
+    if (Ls > 1) {
+      long long M = (long long)Ls * P.R;
+      if (pl.tw[p].reserve(sizeof(cpx) * (size_t)M)) return fail(SGX_ERR_CUDA, "cudaMalloc", "fft twiddles");
+      int blocks = (int)((M + 255) / 256 < 2048 ? (M + 255) / 256 : 2048);
+      SGX_COUNTED_LAUNCH(twiddle_kernel, dim3(blocks), dim3(256), 0, s, pl.tw[p].as<cpx>(), M, Ls, M);
+      P.twg = pl.tw[p].as<cpx>();
+    }
+    Ls *= P.R;
+  }
+  return SGX_OK;
+}
+
+}  // namespace fft
+}  // namespace sgx
