@@ -19,7 +19,7 @@ TRACK_FIELDS = ("absoluteSample", "codeFreq", "carrFreq", "I_P", "I_E", "I_L", "
 SGX_ERR_SHORT = -3
 
 EXPORTS = ("sgx_abi_version", "sgx_last_error", "sgx_device_count", "sgx_set_device",
-           "sgx_kernel_launch_count", "sgx_acquire", "sgx_track", "sgx_synth_generate")
+           "sgx_kernel_launch_count", "sgx_acquire", "sgx_track", "sgx_synth_generate", "sgx_fft_c2c")
 
 
 class NativeError(RuntimeError):
@@ -100,6 +100,17 @@ class Lib(object):
                                 ctypes.byref(pod), _ptr(ca_chips), _ptr(out), _ptr(ms_done),
                                 ctypes.c_void_p(stream))
         return rc, ms_done
+
+    def fft(self, x, inverse=False, stream=0):
+        """Unnormalised FFT of the rows of complex64 x through the acquisition FFT engine (test hook)."""
+        self.require_device()
+        x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.complex64)
+        out = np.empty_like(x)
+        self.dll.sgx_fft_c2c.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32,
+                                         ctypes.c_int32, ctypes.c_void_p]
+        self.check(self.dll.sgx_fft_c2c(_ptr(x), _ptr(out), x.shape[1], x.shape[0], int(bool(inverse)),
+                                        ctypes.c_void_p(stream)))
+        return out
 
     # ------------------------------------------------------------------ synthetic recordings
     def synth(self, out, rec_stride, n_samples, start, specs, bits, lut, ca_chips, stream=0):

@@ -29,6 +29,7 @@ def acquire_batch(signals, settings, prn_first=0, prn_count=None, stream=0, diag
     stride = signals.stride(0) if hasattr(signals, "data_ptr") else signals.strides[0]
     table = np.ascontiguousarray(make_ca_table(settings).astype(np.int8))
     fidx = np.ascontiguousarray(fine_code_index(settings, pod.fineMs))
+    chips = _native.ca_chips_int8()          # named so the buffer outlives the ctypes call
     carr = np.zeros((r, prn_count))
     cph = np.zeros((r, prn_count))
     met = np.zeros((r, prn_count))
@@ -36,7 +37,7 @@ def acquire_batch(signals, settings, prn_first=0, prn_count=None, stream=0, diag
     fine = np.zeros((r, prn_count), dtype=np.int32)
     import ctypes
     rc = L.dll.sgx_acquire(_native._ptr(signals), int(stride), ns, r, ctypes.byref(pod), _native._ptr(table),
-                           _native._ptr(_native.ca_chips_int8()), _native._ptr(fidx), int(prn_first),
+                           _native._ptr(chips), _native._ptr(fidx), int(prn_first),
                            int(prn_count), _native._ptr(carr), _native._ptr(cph), _native._ptr(met),
                            _native._ptr(fbin), _native._ptr(fine), ctypes.c_void_p(stream))
     L.check(rc)

@@ -463,6 +463,12 @@ extern "C" int sgx_acquire(const int8_t* sig, int64_t rec_stride, int64_t n_samp
       codePhase[i] = (double)h_cph[i];                                   // :193
     }
   }
+  if (getenv("SGX_DEBUG")) {
+    long long hs = 0;
+    cudaMemcpy(&hs, a.sums.p, sizeof(hs), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[sgx debug] sum[0]=%lld n=%lld nf=%d nfft=%d npass=%d R=(%d,%d,%d)\n", hs, (long long)n_samples, nf,
+            a.nfft, a.fine.npass, a.fine.pass[0].R, a.fine.pass[1].R, a.fine.pass[2].R);
+  }
   if (nf > 0) {
     const int nt_f = a.fine.pass[a.fine.npass - 1].ntiles;
     const int uniq = a.nfft / 2 + 1;                                      // ceil((nfft+1)/2), :184
@@ -499,5 +505,29 @@ extern "C" int sgx_acquire(const int8_t* sig, int64_t rec_stride, int64_t n_samp
   free(items);
   free(slot);
   free(h_cph);
+  return SGX_OK;
+}
+
+// Test hook: plain complex-to-complex transform of `batch` rows of length n through the same engine
+// (host pointers, interleaved float32 re/im).  Unnormalised in both directions, like numpy's fft and
+// n * ifft.  Exists so that tests can diff the FFT engine alone against numpy.fft.
+extern "C" int sgx_fft_c2c(const float* in, float* out, int32_t n, int32_t batch, int32_t inverse,
+                           void* cuda_stream) {
+  if (sgx_device_count() <= 0) return fail(SGX_ERR_NODEV, "sgx_fft_c2c", "no CUDA device");
+  if (!in || !out || n < 2 || batch < 1) return fail(SGX_ERR_ARG, "sgx_fft_c2c", "bad argument");
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  static fft::Plan pl;   // rebuilt on every call: this is a test hook, not a hot path
+  int rc = fft::build_plan(pl, n, inverse != 0, s);
+  if (rc) return rc;
+  static DevBuf bin, bout, w0, w1;
+  const size_t bytes = sizeof(cpx) * (size_t)n * batch;
+  if (bin.reserve(bytes) || bout.reserve(bytes) || w0.reserve(bytes) || w1.reserve(bytes))
+    return fail(SGX_ERR_CUDA, "cudaMalloc", "fft test buffers");
+  SGX_CUDA(cudaMemcpyAsync(bin.p, in, bytes, cudaMemcpyHostToDevice, s));
+  rc = run_fft(pl, inverse != 0, batch, fft::LoadCpx{bin.as<cpx>(), (long long)n},
+               fft::StoreCpx{bout.as<cpx>(), (long long)n, 1.f, 0}, w0.as<cpx>(), w1.as<cpx>(), s);
+  if (rc) return rc;
+  SGX_CUDA(cudaMemcpyAsync(out, bout.p, bytes, cudaMemcpyDeviceToHost, s));
+  SGX_CUDA(cudaStreamSynchronize(s));
   return SGX_OK;
 }

@@ -53,7 +53,7 @@ def test_function_api_and_channel_table(recordings, capsys):
     ch = preRun(res, s)
     showChannelStatus(ch, s)
     out = capsys.readouterr().out
-    assert "| Channel | PRN |" in out and out.count("Off") == int((ch.PRN == 0).sum())
+    assert "| Channel | PRN |" in out and out.count("|   Off  |") == int((ch.PRN == 0).sum())
 
 
 def test_prn_shards_and_batch_equal_single(recordings):
