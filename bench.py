@@ -1,0 +1,413 @@
+#!/usr/bin/env python
+"""Benchmark of the two hot paths on B200 (one JSON line on stdout, rank 0).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Primary line  : tracking channel-ms/s on BASELINE.json config 4 ("batched tracking: 8 channels x 256
+                independent recordings (37 s each) sharded across 1/2/4/8 GPUs"): every GPU holds
+                256/8 = 32 recordings (45 GB of int8 samples, generated on the device), i.e. weak
+                scaling; N = 8 is the whole configuration.  A step = one pass of sgx_track over the
+                rank's shard (32 x 8 channels x 37000 code periods), input and output resident in HBM.
+`e2e`         : the same shard through the same C-ABI call with HOST (pinned) buffers: the int8
+                recordings are copied host->device and the 13 result series device->host inside the
+                timed region.
+`secondary`   : acquisition search cells/s (config 1 settings, a batch of 11 ms recordings per GPU).
+`roofline`    : tracking kernel, algorithmic bytes (38192 B in + 104 B out per channel-ms,
+                SURVEY.md section 8(d)) / CUDA-event duration vs the measured HBM copy bandwidth.
+`cpu_baseline`: the numpy oracle (a restatement of the reference's loops, oracle/gnss_oracle.py) timed
+                on one host core on a bounded sample.
+`--impl reference` times that CPU path on all host cores (one process per channel / PRN group).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+    os.environ.setdefault(_v, "1")
+
+import numpy as np  # noqa: E402
+
+N_CODE = 38192
+REC_PER_GPU = 32
+CHANNELS = 8
+MS = 37000
+ACQ_REC_PER_GPU = 32
+BYTES_PER_CHANNEL_MS = 38192 + 13 * 8
+FLOP_PER_CELL = 330.0                          # reference formulation, SURVEY.md 8(d)
+TRACK_CPU_MS = 1000                            # bounded CPU sample (code periods per channel)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def mark(self):
+        return len(self.rows)
+
+    def stop(self, lo=0, hi=None):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = self.rows[lo:hi] or self.rows
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ workloads
+def make_specs(first_seed, count):
+    from softgnss_python_b200 import synth
+    return [synth.RecordingSpec(synth.default_constellation(first_seed + r, CHANNELS), seed=first_seed + r)
+            for r in range(count)]
+
+
+def channel_truth(specs):
+    """Channel table as preRun would hand it to tracking: PRN, carrier (with the fine search's -36 Hz
+    bias) and the code phase the acquisition reports (start + 1, A.1-9)."""
+    prn, freq, cph = [], [], []
+    for sp in specs:
+        for i, s in enumerate(sp.sats):
+            prn.append(s.prn)
+            freq.append(sp.true_carr_freq(i) - 36.0)
+            cph.append(float((s.code_phase + 1) % N_CODE))
+    return prn, freq, cph
+
+
+def run_gpu(args, rank, world):
+    import torch
+    import torch.distributed as dist
+    from softgnss_python_b200 import _native, synth
+    from softgnss_python_b200.acquisition import acquire_batch
+    from softgnss_python_b200.settings import Settings, to_pod
+
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L = _native.lib()
+    L.require_device()
+    L.check(L.dll.sgx_set_device(local))
+    stream = torch.cuda.current_stream().cuda_stream
+    chips, lut = _native.ca_chips_int8(), synth.cos_lut()
+
+    recs, ms = args.recordings, args.ms
+    settings = Settings(msToProcess=float(ms))
+    pod = to_pod(settings)
+    specs = make_specs(2000 + rank * recs, recs)
+    n = (ms + 2) * N_CODE
+    stride = (n + 15) // 16 * 16
+    dev = torch.empty((recs, stride), dtype=torch.int8, device="cuda")
+    sp, bits = _native.make_synth_specs(specs)
+    for r0 in range(0, recs, 8):                       # generate on the device, 8 recordings per launch
+        r1 = min(recs, r0 + 8)
+        sub = (_native.SgxSynthSpec * (r1 - r0))(*[sp[i] for i in range(r0, r1)])
+        L.synth(dev[r0:r1], stride, n, 0, sub, np.ascontiguousarray(bits[r0:r1]), lut, chips, stream)
+    chans = _native.make_channels(*channel_truth(specs))
+    out = torch.empty((recs, CHANNELS, 13, ms), dtype=torch.float64, device="cuda")
+    rec_len = [n] * recs
+    units = recs * CHANNELS * ms
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_dev():
+        rc, done = L.track(dev, stride, rec_len, chans, pod, chips, out, stream)
+        L.check(rc)
+        return done
+
+    # ---- device-resident timing (value, roofline) -------------------------------------------------
+    clocks = ClockSampler(local) if rank == 0 else None     # started early: nvidia-smi needs ~1 s to spin up
+    for _ in range(args.warmup):
+        step_dev()
+    barrier()
+    l0 = L.launches()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    c0 = clocks.mark() if clocks else 0
+    ev[0].record()
+    for k in range(args.steps):
+        done = step_dev()
+        ev[k + 1].record()
+    barrier()
+    c1 = clocks.mark() if clocks else 0
+    launches = L.launches() - l0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    assert int(done.min()) == ms
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * units / (ms_per_step / 1e3)
+    kernel_ms = float(np.mean([ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]))
+    lock = out[:, :, 3, 500:].abs().mean().item() / max(out[:, :, 7, 500:].abs().mean().item(), 1e-9) if ms > 600 else None
+
+    # ---- end to end through the C ABI with host buffers --------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        try:
+            host = torch.empty((recs, stride), dtype=torch.int8, pin_memory=True)
+            host.copy_(dev)
+            hout = torch.empty((recs, CHANNELS, 13, ms), dtype=torch.float64, pin_memory=True)
+            del dev
+            torch.cuda.empty_cache()
+            hin, hres = host.numpy(), hout.numpy()
+
+            def step_host():
+                rc, d = L.track(hin, stride, rec_len, chans, pod, chips, hres, stream)
+                L.check(rc)
+
+            for _ in range(max(1, min(args.warmup, 2))):
+                step_host()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ksteps = max(1, min(args.steps, 3))
+            e0.record()
+            for _ in range(ksteps):
+                step_host()
+            e1.record()
+            barrier()
+            tt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e_ms = float(tt.item()) / ksteps
+            e2e = {"value": world * units / (e2e_ms / 1e3), "unit": "channel-ms/s",
+                   "h2d_bytes_per_step": int(recs * n), "d2h_bytes_per_step": int(hres.nbytes),
+                   "ms_per_step": e2e_ms, "steps": ksteps}
+            del host, hout
+        except Exception as exc:  # pinned allocation can fail on a small host
+            e2e = {"value": None, "unit": "channel-ms/s", "error": str(exc)[:200]}
+
+    # ---- secondary: acquisition ----------------------------------------------------------------------
+    acq = None
+    if not args.no_acq:
+        areq = args.acq_recordings
+        aspecs = make_specs(1000 + rank * areq, areq)
+        an = 11 * N_CODE
+        adev = torch.empty((areq, an), dtype=torch.int8, device="cuda")
+        asp, abits = _native.make_synth_specs(aspecs)
+        L.synth(adev, an, an, 0, asp, abits, lut, chips, stream)
+        aset = Settings()
+        cells = areq * 32 * 29 * N_CODE
+        for _ in range(args.warmup):
+            res = acquire_batch(adev, aset, stream=stream)
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        al0 = L.launches()
+        a0.record()
+        for _ in range(args.steps):
+            res = acquire_batch(adev, aset, stream=stream)
+        a1.record()
+        barrier()
+        alaunch = L.launches() - al0
+        ta = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ta, op=dist.ReduceOp.MAX)
+        a_ms = float(ta.item()) / args.steps
+        ahost = torch.empty((areq, an), dtype=torch.int8, pin_memory=True)
+        ahost.copy_(adev)
+        ah = ahost.numpy()
+        acquire_batch(ah, aset, stream=stream)
+        barrier()
+        a0.record()
+        for _ in range(args.steps):
+            acquire_batch(ah, aset, stream=stream)
+        a1.record()
+        barrier()
+        tb = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        ae_ms = float(tb.item()) / args.steps
+        truth = sum(len(s.sats) for s in aspecs)
+        acq = {"metric": "acq search cells/s", "value": world * cells / (a_ms / 1e3), "unit": "cells/s",
+               "ms_per_step": a_ms, "gpu_launches": int(alaunch),
+               "config": {"workload": "config 1 settings (32 PRN x 29 bins x 38192 code phases + fine search), "
+                                      "%d x 11 ms recordings per GPU, 8 satellites each at 45 dB-Hz" % areq,
+                          "detected": int((res["carrFreq"] > 0).sum()), "present": truth},
+               "e2e": {"value": world * cells / (ae_ms / 1e3), "unit": "cells/s",
+                       "h2d_bytes_per_step": int(areq * an), "d2h_bytes_per_step": int(areq * 32 * 3 * 8)},
+               "roofline": {"bound": "fp32 (CUDA-core FFT; not HBM: 0.3 B/cell)",
+                            "achieved": world * cells * FLOP_PER_CELL / (a_ms / 1e3) / 1e12 / world,
+                            "peak": 74.5, "unit": "TFLOP/s",
+                            "frac": cells * FLOP_PER_CELL / (a_ms / 1e3) / 1e12 / 74.5,
+                            "note": "reference-formulation FLOPs (330/cell); peak = nominal 148 SM x 128 x 2 x 1.965 GHz"}}
+
+    ck = clocks.stop(c0, c1) if clocks else None
+    if world > 1:
+        counts = [None] * world
+        dist.all_gather_object(counts, int(done.sum()))          # the only collective: gather of results
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    peak, how = peaks()
+    achieved = units * BYTES_PER_CHANNEL_MS / (kernel_ms / 1e3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "track_traffic.json")
+    if os.path.exists(tp):
+        tj = json.load(open(tp))
+        if tj.get("recordings") == recs and tj.get("ms") == ms:
+            traffic = tj.get("dram_bytes_per_launch")
+    line = {
+        "metric": "tracking channel-ms/s", "value": value, "unit": "channel-ms/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 correlators / f64 loop filters", "data": "synthetic",
+        "realtime_factor": value / 1000.0,
+        "config": {"workload": "BASELINE config 4 shard: %d recordings x %d channels x %d ms per GPU "
+                               "(int8 IF, fs 38.192 MHz, generated on device); x%d GPUs" % (recs, CHANNELS, ms, world),
+                   "recordings_per_gpu": recs, "channels": CHANNELS, "ms": ms,
+                   "l2": "inputs (%.1f GB per GPU) far exceed L2; no flush needed" % (recs * n / 1e9),
+                   "lock_check_mean_absIP_over_absQP": lock},
+        "gpu_launches": int(launches),
+        "e2e": e2e,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "kernel": "sgx::track_kernel", "kernel_ms": kernel_ms,
+                     "algorithmic_bytes_per_channel_ms": BYTES_PER_CHANNEL_MS, "peak_source": how},
+        "clocks": ck,
+        "secondary": acq,
+    }
+    if not args.no_cpu:
+        line["cpu_baseline"] = cpu_track_baseline(TRACK_CPU_MS, 1)
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ CPU arms
+_CPU = {}
+
+
+def _cpu_prepare(ms):
+    """One config-4 recording (seed 2000) long enough for `ms` code periods; shared with forked workers."""
+    if _CPU.get("ms") == ms:
+        return
+    from softgnss_python_b200 import synth
+    from softgnss_python_b200.settings import Settings
+    spec = make_specs(2000, 1)[0]
+    _CPU.update(ms=ms, data=synth.generate_cpu(spec, (ms + 2) * N_CODE), truth=channel_truth([spec]),
+                settings=Settings(msToProcess=float(ms)))
+
+
+def _cpu_track_one(ch):
+    from oracle import gnss_oracle as orc
+    prn, freq, cph = _CPU["truth"]
+    t = time.perf_counter()
+    _, done = orc.track_channel(_CPU["data"], prn[ch], freq[ch], cph[ch], _CPU["settings"], _CPU["ms"])
+    assert done == _CPU["ms"]
+    return time.perf_counter() - t
+
+
+def cpu_track_baseline(ms, procs):
+    """Oracle tracking (numpy restatement of tracking.py:132-275).  procs == 1: the 8 channels of one
+    recording one after the other on one core (as the reference does); procs > 1: one channel per process."""
+    import multiprocessing as mp
+    _cpu_prepare(ms)
+    if procs == 1:
+        dt = sum(_cpu_track_one(c) for c in range(CHANNELS))
+        n_ch = CHANNELS
+    else:
+        with mp.get_context("fork").Pool(procs) as pool:
+            pool.map(_cpu_track_one, [0] * procs)      # start the workers before timing
+            t = time.perf_counter()
+            pool.map(_cpu_track_one, [c % CHANNELS for c in range(procs)], chunksize=1)
+            dt = time.perf_counter() - t
+        n_ch = procs
+    return {"value": n_ch * ms / dt, "unit": "channel-ms/s", "cores": procs, "kind": "port",
+            "sample": "%d channel(s) x %d ms of config-4 recording seed 2000, oracle/gnss_oracle.py "
+                      "(numpy restatement of the reference loop; numpy %s)" % (n_ch, ms, np.__version__)}
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU algorithm (oracle port) on all host cores."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 64))
+    vals = []
+    for k in range(args.warmup + args.steps):
+        r = cpu_track_baseline(args.ref_ms, procs)
+        if k >= args.warmup:
+            vals.append(r)
+    v = float(np.mean([x["value"] for x in vals]))
+    base = vals[-1]
+    base["value"] = v
+    line = {"impl": "reference", "metric": "tracking channel-ms/s", "value": v, "unit": "channel-ms/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": procs * args.ref_ms / v * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "BASELINE config 4 shard: %d recordings x %d channels x %d ms per GPU; CPU arm "
+                                   "runs a bounded sample of it" % (REC_PER_GPU, CHANNELS, MS)},
+            "cpu_baseline": base,
+            "e2e": {"value": v, "unit": "channel-ms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--recordings", type=int, default=REC_PER_GPU, help="recordings per GPU")
+    ap.add_argument("--ms", type=int, default=MS)
+    ap.add_argument("--acq-recordings", type=int, default=ACQ_REC_PER_GPU)
+    ap.add_argument("--ref-ms", type=int, default=400, help="code periods per channel per CPU step")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-acq", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    run_gpu(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -16,6 +16,20 @@ from .settings import fine_code_index, make_ca_table, to_pod
 from .tracking import Result
 
 
+_TABLES = {}
+
+
+def _tables(settings, fine_ms):
+    """Host-built tables (A3 code table, A10 chip index, C/A chips), cached per signal definition."""
+    key = (float(settings.samplingFreq), float(settings.codeFreqBasis), int(settings.codeLength), int(fine_ms))
+    if key not in _TABLES:
+        _TABLES.clear()
+        _TABLES[key] = (np.ascontiguousarray(make_ca_table(settings).astype(np.int8)),
+                        np.ascontiguousarray(fine_code_index(settings, fine_ms)),
+                        _native.ca_chips_int8())
+    return _TABLES[key]
+
+
 def acquire_batch(signals, settings, prn_first=0, prn_count=None, stream=0, diagnostics=False):
     """``signals``: int8 [R, n_samples] (numpy or CUDA tensor).  Searches PRN indices
     [prn_first, prn_first+prn_count) for every recording; returns dict of float64 [R, prn_count]."""
@@ -27,9 +41,7 @@ def acquire_batch(signals, settings, prn_first=0, prn_count=None, stream=0, diag
         prn_count = nsat - prn_first
     r, ns = int(signals.shape[0]), int(signals.shape[1])
     stride = signals.stride(0) if hasattr(signals, "data_ptr") else signals.strides[0]
-    table = np.ascontiguousarray(make_ca_table(settings).astype(np.int8))
-    fidx = np.ascontiguousarray(fine_code_index(settings, pod.fineMs))
-    chips = _native.ca_chips_int8()          # named so the buffer outlives the ctypes call
+    table, fidx, chips = _tables(settings, pod.fineMs)   # named: the buffers must outlive the ctypes call
     carr = np.zeros((r, prn_count))
     cph = np.zeros((r, prn_count))
     met = np.zeros((r, prn_count))

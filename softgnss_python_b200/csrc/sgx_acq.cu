@@ -27,12 +27,17 @@ struct ProNco {  // A6: int8 sample x (sin + j cos) of bin k; batch = (rec*block
   long long rec_stride;
   const double* cps;  // [nbins] carrier cycles per sample = f_k / fs
   int nbins, blocks, n;
-  __device__ __forceinline__ cpx load(int batch, int i) const {
+  double cps_bin;
+  __device__ __forceinline__ void prepare(int batch) {
     const int bin = batch % nbins;
     const int rb = batch / nbins;
     const int blk = rb % blocks, rec = rb / blocks;
-    const float x = (float)sig[(long long)rec * rec_stride + (long long)blk * n + i];
-    double ph = (double)i * cps[bin];
+    sig += (long long)rec * rec_stride + (long long)blk * n;
+    cps_bin = cps[bin];
+  }
+  __device__ __forceinline__ cpx load(int i) const {
+    const float x = (float)sig[i];
+    double ph = (double)i * cps_bin;
     ph -= rint(ph);
     float s, c;
     sincospif(2.0f * (float)ph, &s, &c);
@@ -43,9 +48,8 @@ struct ProNco {  // A6: int8 sample x (sin + j cos) of bin k; batch = (rec*block
 struct ProCode {  // A5: row of the sampled C/A table (tiled over coherent ms), real input
   const int8_t* table;  // [32][n1]
   int n1;
-  __device__ __forceinline__ cpx load(int prn, int i) const {
-    return make_float2((float)table[(long long)prn * n1 + (i % n1)], 0.f);
-  }
+  __device__ __forceinline__ void prepare(int prn) { table += (long long)prn * n1; }
+  __device__ __forceinline__ cpx load(int i) const { return make_float2((float)table[i % n1], 0.f); }
 };
 
 struct SearchDims {
@@ -58,16 +62,16 @@ struct ProMul {  // A7 first half: spectrum x conj(code spectrum); batch -> item
   SearchDims d;
   int n;
   long long item0;
-  __device__ __forceinline__ cpx load(int batch, int i) const {
+  __device__ __forceinline__ void prepare(int batch) {
     long long item = item0 + batch;
     const int blk = (int)(item % d.blocks); item /= d.blocks;
     const int bin = (int)(item % d.nbins); item /= d.nbins;
     const int prn = (int)(item % d.nprn);
     const int rec = (int)(item / d.nprn);
-    const cpx a = spec[(((long long)rec * d.blocks + blk) * d.nbins + bin) * n + i];
-    const cpx b = codeF[(long long)(d.prn_first + prn) * n + i];
-    return fft::cmulf(a, b);
+    spec += (((long long)rec * d.blocks + blk) * d.nbins + bin) * n;
+    codeF += (long long)(d.prn_first + prn) * n;
   }
+  __device__ __forceinline__ cpx load(int i) const { return fft::cmulf(spec[i], codeF[i]); }
 };
 
 struct PeakSel {  // per (rec, prn): result of A8/A9 first half
@@ -81,13 +85,13 @@ struct ProMulSel {  // same product for the winning (bin, block) of PRN item (re
   const PeakSel* sel;
   SearchDims d;
   int n;
-  __device__ __forceinline__ cpx load(int batch, int i) const {
+  __device__ __forceinline__ void prepare(int batch) {
     const PeakSel s = sel[batch];
     const int prn = batch % d.nprn, rec = batch / d.nprn;
-    const cpx a = spec[(((long long)rec * d.blocks + s.blk) * d.nbins + s.bin) * n + i];
-    const cpx b = codeF[(long long)(d.prn_first + prn) * n + i];
-    return fft::cmulf(a, b);
+    spec += (((long long)rec * d.blocks + s.blk) * d.nbins + s.bin) * n;
+    codeF += (long long)(d.prn_first + prn) * n;
   }
+  __device__ __forceinline__ cpx load(int i) const { return fft::cmulf(spec[i], codeF[i]); }
 };
 
 struct FineItem {
@@ -103,12 +107,16 @@ struct ProFine {  // A10: (x - mean) * code, zero padded
   const unsigned short* idx;  // [nvalid]
   const FineItem* items;
   int nvalid;
-  __device__ __forceinline__ cpx load(int batch, int i) const {
-    if (i >= nvalid) return make_float2(0.f, 0.f);
+  float mean;
+  __device__ __forceinline__ void prepare(int batch) {
     const FineItem it = items[batch];
-    const float mean = (float)((double)sums[it.rec] / (double)n_samples);
-    const float x = (float)sig[(long long)it.rec * rec_stride + it.codePhase + i] - mean;
-    return make_float2(x * (float)chips[it.prn * 1023 + idx[i]], 0.f);
+    mean = (float)((double)sums[it.rec] / (double)n_samples);
+    sig += (long long)it.rec * rec_stride + it.codePhase;
+    chips += it.prn * 1023;
+  }
+  __device__ __forceinline__ cpx load(int i) const {
+    if (i >= nvalid) return make_float2(0.f, 0.f);
+    return make_float2(((float)sig[i] - mean) * (float)chips[idx[i]], 0.f);
   }
 };
 
@@ -118,8 +126,8 @@ struct EpiPeak {  // |.|^2 and arg-max of the whole row; one key per (item, tile
   int ntiles;
   long long item0;
   unsigned long long best;
-  __device__ __forceinline__ void begin() { best = 0ull; }
-  __device__ __forceinline__ void put(int, int i, cpx v) {
+  __device__ __forceinline__ void begin(int) { best = 0ull; }
+  __device__ __forceinline__ void put(int i, cpx v) {
     const float mag = fmaf(v.x, v.x, v.y * v.y);
     const unsigned long long k = fft::peak_key(mag, (unsigned)i);
     best = k > best ? k : best;
@@ -146,9 +154,10 @@ struct EpiSecond {  // arg-max over the candidates only
   const PeakSel* sel;
   int ntiles, chip, n;
   unsigned long long best;
-  __device__ __forceinline__ void begin() { best = 0ull; }
-  __device__ __forceinline__ void put(int batch, int i, cpx v) {
-    if (!second_peak_candidate(i, sel[batch].codePhase, chip, n)) return;
+  int cp;
+  __device__ __forceinline__ void begin(int batch) { best = 0ull; cp = sel[batch].codePhase; }
+  __device__ __forceinline__ void put(int i, cpx v) {
+    if (!second_peak_candidate(i, cp, chip, n)) return;
     const float mag = fmaf(v.x, v.x, v.y * v.y);
     const unsigned long long k = fft::peak_key(mag, (unsigned)i);
     best = k > best ? k : best;
@@ -163,8 +172,8 @@ struct EpiFine {  // acquisition.py:186-187: arg-max over fftxc[4 : uniq-5], ind
   unsigned long long* partial;
   int ntiles, lo, hi;  // candidates lo <= k < hi
   unsigned long long best;
-  __device__ __forceinline__ void begin() { best = 0ull; }
-  __device__ __forceinline__ void put(int, int i, cpx v) {
+  __device__ __forceinline__ void begin(int) { best = 0ull; }
+  __device__ __forceinline__ void put(int i, cpx v) {
     if (i < lo || i >= hi) return;
     const float mag = fmaf(v.x, v.x, v.y * v.y);
     const unsigned long long k = fft::peak_key(mag, (unsigned)(i - lo));
@@ -298,8 +307,11 @@ struct AcqPlan {
 static AcqPlan g_acq;
 
 static unsigned long long fnv(const void* p, size_t n, unsigned long long h = 1469598103934665603ULL) {
+  // FNV-1a over 64-bit words (the tables are MBs; this runs on every call to validate the plan cache)
   const unsigned char* b = (const unsigned char*)p;
-  for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ULL; }
+  size_t i = 0;
+  for (; i + 8 <= n; i += 8) { unsigned long long w; memcpy(&w, b + i, 8); h ^= w; h *= 1099511628211ULL; }
+  for (; i < n; ++i) { h ^= b[i]; h *= 1099511628211ULL; }
   return h;
 }
 
@@ -413,7 +425,7 @@ extern "C" int sgx_acquire(const int8_t* sig, int64_t rec_stride, int64_t n_samp
   // ---- A6 + forward half of A7: one spectrum per (rec, block, bin) -----------------------------
   if (nspec > 32768 || npr > 32768)
     return fail(SGX_ERR_ARG, "sgx_acquire", "too many recordings in one call (split the batch)");
-  rc = run_fft(a.fwd, false, nspec, ProNco{d_sig, stride, a.cps.as<double>(), nbins, blocks, (int)n},
+  rc = run_fft(a.fwd, false, nspec, ProNco{d_sig, stride, a.cps.as<double>(), nbins, blocks, (int)n, 0.0},
                fft::StoreCpx{a.spec.as<cpx>(), n, 1.f, 0}, a.work0.as<cpx>(), a.work1.as<cpx>(), s);
   if (rc) return rc;
   // ---- A7: spectrum x code -> IFFT -> |.|^2 -> per-row arg-max, in L2-sized chunks -------------
@@ -431,7 +443,7 @@ extern "C" int sgx_acquire(const int8_t* sig, int64_t rec_stride, int64_t n_samp
   {
     EpiSecond es;
     es.partial = a.partial2.as<unsigned long long>(); es.sel = a.sel.as<PeakSel>(); es.ntiles = nt_last;
-    es.chip = st->samplesPerCodeChip; es.n = (int)n; es.best = 0;
+    es.chip = st->samplesPerCodeChip; es.n = (int)n; es.best = 0; es.cp = 0;
     rc = run_fft(a.inv, true, npr, ProMulSel{a.spec.as<cpx>(), a.codeF.as<cpx>(), a.sel.as<PeakSel>(), d, (int)n}, es,
                  a.work0.as<cpx>(), a.work1.as<cpx>(), s);
     if (rc) return rc;
@@ -485,7 +497,7 @@ extern "C" int sgx_acquire(const int8_t* sig, int64_t rec_stride, int64_t n_samp
       ef.partial = a.fpartial.as<unsigned long long>() + (size_t)f0 * nt_f; ef.ntiles = nt_f; ef.lo = 4;
       ef.hi = uniq - 5; ef.best = 0;
       ProFine pf{d_sig, stride, (const long long*)a.sums.p, (long long)n_samples, a.chips.as<int8_t>(),
-                 a.fidx.as<unsigned short>(), a.fitems.as<FineItem>() + f0, a.nvalid};
+                 a.fidx.as<unsigned short>(), a.fitems.as<FineItem>() + f0, a.nvalid, 0.f};
       rc = run_fft(a.fine, false, cnt, pf, ef, a.work0.as<cpx>(), a.work1.as<cpx>(), s);
       if (rc) return rc;
     }

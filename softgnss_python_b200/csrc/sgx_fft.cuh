@@ -111,20 +111,24 @@ template <bool INV> struct Dft<7, INV> { static __device__ __forceinline__ void 
 template <bool INV> struct Dft<11, INV> { static __device__ __forceinline__ void run(cpx* v) { dft_prime<11, INV>(v, COS11, SIN11); } };
 template <bool INV> struct Dft<31, INV> { static __device__ __forceinline__ void run(cpx* v) { dft_prime<31, INV>(v, COS31, SIN31); } };
 
-// One Stockham sub-pass of radix r over the R x T tile held in shared memory (row stride TP).
+constexpr int TILE = 16;        // columns per CTA: 16 x 8 B = one 128-byte line per row
+constexpr int TILE_P = TILE + 1;  // padded row stride in shared memory
+constexpr int ROWS_PER_ITER = FFT_THREADS / TILE;
+
+// One Stockham sub-pass of radix r over the R x TILE tile held in shared memory.
 template <int r, bool INV>
 __device__ __forceinline__ void subpass(const cpx* __restrict__ in, cpx* __restrict__ out,
-                                        const cpx* __restrict__ W, int R, int ls, int T, int TP) {
+                                        const cpx* __restrict__ W, int R, int ls) {
   const int mm = R / r;
-  const int total = mm * T;
+  const int total = mm * TILE;
   const int wstride = R / (ls * r);
   for (int idx = threadIdx.x; idx < total; idx += FFT_THREADS) {
-    const int jj = idx % T;
-    const int b = idx / T;
-    const int kk = b % ls;
+    const int jj = idx & (TILE - 1);
+    const int b = idx / TILE;
+    const int kk = ls > 1 ? b % ls : 0;
     cpx v[r];
 #pragma unroll
-    for (int u = 0; u < r; ++u) v[u] = in[(b + u * mm) * TP + jj];
+    for (int u = 0; u < r; ++u) v[u] = in[(b + u * mm) * TILE_P + jj];
     if (ls > 1) {
 #pragma unroll
       for (int u = 1; u < r; ++u) v[u] = cmulf(v[u], W[u * kk * wstride]);
@@ -132,62 +136,76 @@ __device__ __forceinline__ void subpass(const cpx* __restrict__ in, cpx* __restr
     Dft<r, INV>::run(v);
     const int base = (b - kk) * r + kk;
 #pragma unroll
-    for (int u = 0; u < r; ++u) out[(base + u * ls) * TP + jj] = v[u];
+    for (int u = 0; u < r; ++u) out[(base + u * ls) * TILE_P + jj] = v[u];
   }
 }
 
 template <bool INV, bool BIG>
-__device__ __forceinline__ void run_subpass(int r, const cpx* in, cpx* out, const cpx* W, int R, int ls,
-                                            int T, int TP) {
+__device__ __forceinline__ void run_subpass(int r, const cpx* in, cpx* out, const cpx* W, int R, int ls) {
   switch (r) {
-    case 2: subpass<2, INV>(in, out, W, R, ls, T, TP); break;
-    case 4: subpass<4, INV>(in, out, W, R, ls, T, TP); break;
-    case 8: subpass<8, INV>(in, out, W, R, ls, T, TP); break;
-    case 16: subpass<16, INV>(in, out, W, R, ls, T, TP); break;
+    case 2: subpass<2, INV>(in, out, W, R, ls); break;
+    case 4: subpass<4, INV>(in, out, W, R, ls); break;
+    case 8: subpass<8, INV>(in, out, W, R, ls); break;
+    case 16: subpass<16, INV>(in, out, W, R, ls); break;
     default:
       if (BIG) {
         switch (r) {
-          case 3: subpass<3, INV>(in, out, W, R, ls, T, TP); break;
-          case 5: subpass<5, INV>(in, out, W, R, ls, T, TP); break;
-          case 7: subpass<7, INV>(in, out, W, R, ls, T, TP); break;
-          case 11: subpass<11, INV>(in, out, W, R, ls, T, TP); break;
-          case 31: subpass<31, INV>(in, out, W, R, ls, T, TP); break;
+          case 3: subpass<3, INV>(in, out, W, R, ls); break;
+          case 5: subpass<5, INV>(in, out, W, R, ls); break;
+          case 7: subpass<7, INV>(in, out, W, R, ls); break;
+          case 11: subpass<11, INV>(in, out, W, R, ls); break;
+          case 31: subpass<31, INV>(in, out, W, R, ls); break;
         }
       }
   }
 }
 
-// Pro:  cpx load(int batch, int n)                  -- element n of transform `batch`
-// Epi:  void begin(); void put(int batch, int n, cpx v); void finish(int batch, int tile)
+// Pro:  void prepare(int batch);  cpx load(int n)            -- element n of transform `batch`
+// Epi:  void begin(int batch);    void put(int n, cpx v);    void finish(int batch, int tile)
+// Every thread owns one column (jj = tid % 16) for the whole kernel, so all index arithmetic that
+// depends on the column or on the batch is done once.
 template <class Pro, class Epi, bool INV, bool BIG>
 __global__ void __launch_bounds__(FFT_THREADS) fft_pass_kernel(Pass P, Pro pro, Epi epi) {
   SGX_DYN_SMEM(smem);
-  const int R = P.R, T = P.T, TP = T + 1, m = P.m, Ls = P.Ls;
+  const int R = P.R, m = P.m, Ls = P.Ls;
   cpx* A = reinterpret_cast<cpx*>(smem);
-  cpx* B = A + R * TP;
-  cpx* W = B + R * TP;
+  cpx* B = A + R * TILE_P;
+  cpx* W = B + R * TILE_P;
   const int tid = threadIdx.x;
   const int tile = blockIdx.x;
-  const int batch = blockIdx.y + gridDim.y * blockIdx.z;
-  const int j0 = tile * T;
+  const int batch = blockIdx.y;
+  const int j0 = tile * TILE;
+  const int jj = tid & (TILE - 1), t0 = tid / TILE;
+  const int j = j0 + jj;
+  const bool valid = j < m;
+  const int k = Ls > 1 ? j % Ls : 0;
 
+  pro.prepare(batch);
   for (int q = tid; q < R; q += FFT_THREADS) {
     cpx w = P.wr[q];
     if (INV) w.y = -w.y;
     W[q] = w;
   }
-  for (int e = tid; e < R * T; e += FFT_THREADS) {
-    const int jj = e % T, t = e / T, j = j0 + jj;
-    cpx v = make_float2(0.f, 0.f);
-    if (j < m) {
-      v = pro.load(batch, j + t * m);
-      if (Ls > 1 && t > 0) {
-        cpx w = P.twg[(size_t)t * Ls + (j % Ls)];
+  if (Ls > 1) {
+    const cpx* tw = P.twg + k;
+#pragma unroll 4
+    for (int t = t0; t < R; t += ROWS_PER_ITER) {
+      cpx v = make_float2(0.f, 0.f);
+      if (valid) {
+        v = pro.load(j + t * m);
+        cpx w = tw[(size_t)t * Ls];
         if (INV) w.y = -w.y;
         v = cmulf(v, w);
       }
+      A[t * TILE_P + jj] = v;
     }
-    A[t * TP + jj] = v;
+  } else {
+#pragma unroll 4
+    for (int t = t0; t < R; t += ROWS_PER_ITER) {
+      cpx v = make_float2(0.f, 0.f);
+      if (valid) v = pro.load(j + t * m);
+      A[t * TILE_P + jj] = v;
+    }
   }
   __syncthreads();
   cpx* src = A;
@@ -195,26 +213,23 @@ __global__ void __launch_bounds__(FFT_THREADS) fft_pass_kernel(Pass P, Pro pro, 
   int ls = 1;
   for (int s = 0; s < P.nsub; ++s) {
     const int r = P.radix[s];
-    run_subpass<INV, BIG>(r, src, dst, W, R, ls, T, TP);
+    run_subpass<INV, BIG>(r, src, dst, W, R, ls);
     ls *= r;
     __syncthreads();
     cpx* tmp = src; src = dst; dst = tmp;
   }
-  epi.begin();
+  epi.begin(batch);
   if (Ls == 1) {
-    // y[j*R + u]: contiguous in u for one column
-    for (int e = tid; e < R * T; e += FFT_THREADS) {
-      const int u = e % R, jj = e / R, j = j0 + jj;
-      if (j < m) epi.put(batch, j * R + u, src[u * TP + jj]);
+    // y[j*R + u]: one column is R contiguous outputs
+    const int ncol = min(TILE, m - j0);
+    for (int c = 0; c < ncol; ++c) {
+      const int base = (j0 + c) * R;
+      for (int u = tid; u < R; u += FFT_THREADS) epi.put(base + u, src[u * TILE_P + c]);
     }
-  } else {
-    for (int e = tid; e < R * T; e += FFT_THREADS) {
-      const int jj = e % T, u = e / T, j = j0 + jj;
-      if (j < m) {
-        const int k = j % Ls;
-        epi.put(batch, (j - k) * R + k + u * Ls, src[u * TP + jj]);
-      }
-    }
+  } else if (valid) {
+    const int base = (j - k) * R + k;
+#pragma unroll 4
+    for (int u = t0; u < R; u += ROWS_PER_ITER) epi.put(base + u * Ls, src[u * TILE_P + jj]);
   }
   epi.finish(batch, tile);
 }
@@ -223,16 +238,17 @@ __global__ void __launch_bounds__(FFT_THREADS) fft_pass_kernel(Pass P, Pro pro, 
 struct LoadCpx {  // plain complex input, transforms `stride` apart
   const cpx* in;
   long long stride;
-  __device__ __forceinline__ cpx load(int batch, int n) const { return in[(long long)batch * stride + n]; }
+  __device__ __forceinline__ void prepare(int batch) { in += (long long)batch * stride; }
+  __device__ __forceinline__ cpx load(int n) const { return in[n]; }
 };
 struct StoreCpx {
   cpx* out;
   long long stride;
   float scale;   // applied to both parts
   int conj;      // store the conjugate
-  __device__ __forceinline__ void begin() {}
-  __device__ __forceinline__ void put(int batch, int n, cpx v) const {
-    out[(long long)batch * stride + n] = make_float2(v.x * scale, conj ? -v.y * scale : v.y * scale);
+  __device__ __forceinline__ void begin(int batch) { out += (long long)batch * stride; }
+  __device__ __forceinline__ void put(int n, cpx v) const {
+    out[n] = make_float2(v.x * scale, conj ? -v.y * scale : v.y * scale);
   }
   __device__ __forceinline__ void finish(int, int) {}
 };
@@ -364,10 +380,10 @@ inline int build_plan(Plan& pl, int N, bool inverse, cudaStream_t s, int maxR = 
     }
     P.Ls = Ls;
     P.m = N / P.R;
-    P.T = 16;
-    P.ntiles = (P.m + P.T - 1) / P.T;
+    P.T = TILE;
+    P.ntiles = (P.m + TILE - 1) / TILE;
     P.inverse = inverse ? 1 : 0;
-    pl.smem[p] = sizeof(cpx) * ((size_t)2 * P.R * (P.T + 1) + P.R);
+    pl.smem[p] = sizeof(cpx) * ((size_t)2 * P.R * TILE_P + P.R);
     if (pl.wr[p].reserve(sizeof(cpx) * P.R)) return fail(SGX_ERR_CUDA, "cudaMalloc", "fft tables");
     SGX_COUNTED_LAUNCH(twiddle_kernel, dim3(4), dim3(128), 0, s, pl.wr[p].as<cpx>(), (long long)P.R, 0, (long long)P.R);
     P.wr = pl.wr[p].as<cpx>();
