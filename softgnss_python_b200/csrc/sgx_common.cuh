@@ -112,8 +112,8 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, unsi
 // all threads: wait until phase `parity` of the barrier has completed
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
 #ifdef SGX_EMUL
-  (void)bar;
-  (void)parity;  // bulk_load completed synchronously
+  // bulk_load bumps the completed-phase count; phase `parity` is done once the count's low bit differs
+  while ((*(volatile unsigned long long*)bar & 1ull) == (unsigned long long)parity) sgx_emul::yield_to_sched();
 #else
   unsigned b = (unsigned)__cvta_generic_to_shared(bar);
   asm volatile(
@@ -131,6 +131,12 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+  return v;
+}
+
+__device__ __forceinline__ double warp_sum_f64(double v) {
 #pragma unroll
   for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
   return v;

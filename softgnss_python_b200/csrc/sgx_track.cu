@@ -111,6 +111,20 @@ __device__ __forceinline__ float byte_to_float(unsigned u_offset_binary, int k) 
   return __uint_as_float(r) - 8388736.0f;
 }
 
+// e^{j 2 pi cyc} in float32 from a float64 phase in cycles.  The phase is reduced in float64 and split
+// into a float32 head and tail; the tail enters to first order, so the result carries only the
+// rounding of its two components (6e-8) instead of the 3e-8-cycle rounding of the argument -- which
+// would otherwise be multiplied by k in every power w^k built from it.
+__device__ __forceinline__ void cis_cycles(double cyc, float& c, float& s) {
+  cyc -= rint(cyc);
+  const float hi = (float)cyc;
+  const float lo = (float)(cyc - (double)hi) * 6.2831853071795865f;
+  float s0, c0;
+  sincospif(2.0f * hi, &s0, &c0);
+  c = fmaf(-s0, lo, c0);
+  s = fmaf(c0, lo, s0);
+}
+
 __device__ __forceinline__ void cmul(float& r, float& i, float ar, float ai, float br, float bi) {
   r = fmaf(ar, br, -(ai * bi));
   i = fmaf(ar, bi, ai * br);
@@ -140,20 +154,278 @@ __device__ void prepare_period(const TrackArgs& a, LoopState& st, long long rec_
   nextRemCode = (lin_y(blk - 1, p.stepP, p.startP) + step) - 1023.0;  // :190
   double w = st.carrFreq * 2.0 * PI;                                  // :195
   double arg_end = w * ((double)blk / a.fs) + st.remCarrPhase;
-  double m = fmod(arg_end, TWO_PI);                                   // :197 (np.remainder)
-  if (m != 0.0 && m < 0.0) m += TWO_PI;
+  double m;                                                           // :197 (np.remainder)
+  if (arg_end >= 0.0) {
+    // exact remainder without the iterative fmod: with the right integer quotient the fused
+    // multiply-add returns x - q*y exactly (the result of fmod is always representable)
+    double q = floor(arg_end * 0.15915494309189535);
+    m = __fma_rn(-q, TWO_PI, arg_end);
+    if (m < 0.0) { q -= 1.0; m = __fma_rn(-q, TWO_PI, arg_end); }
+    else if (m >= TWO_PI) { q += 1.0; m = __fma_rn(-q, TWO_PI, arg_end); }
+  } else {
+    m = fmod(arg_end, TWO_PI);
+    if (m != 0.0 && m < 0.0) m += TWO_PI;
+  }
   nextRemCarr = m;
   p.cps = (w / a.fs) * 0.15915494309189535;
   p.rem_cyc = st.remCarrPhase * 0.15915494309189535;
 }
 
-template <bool BULK>
+// ---- correlate, variant A: contiguous run of aligned 16-sample groups per thread (any sampling rate)
+__device__ __forceinline__ void correlate_groups(const MsParams& P, const int8_t* cur, const float* codeS, int tid,
+                                                 double& tEr, double& tEi, double& tPr, double& tPi, double& tLr,
+                                                 double& tLi) {
+    const int off = (int)(P.pos - (P.pos & ~15LL));
+    const int ng = (off + P.blk + 15) >> 4;
+    const int gpt = (ng + TRK_THREADS - 1) / TRK_THREADS;
+    const int g0 = tid * gpt;
+    const int g1 = min(g0 + gpt, ng);
+    if (g0 < g1) {
+      int ib = 16 * g0 - off;
+      const int i0 = max(ib, 0);
+      CodeVar E, Pm, L;
+      E.init(i0, P.startE, P.stepE, P.inv_step, codeS);
+      Pm.init(i0, P.startP, P.stepP, P.inv_step, codeS);
+      L.init(i0, P.startL, P.stepL, P.inv_step, codeS);
+      // carrier: rot = e^{j theta(ib)}, w[k] = e^{j k dtheta}
+      float wr[16], wi[16], w16r, w16i, rotr, roti;
+      {
+        cis_cycles((double)ib * P.cps + P.rem_cyc, rotr, roti);
+        float s1, c1;
+        cis_cycles(P.cps, c1, s1);
+        wr[0] = 1.f; wi[0] = 0.f; wr[1] = c1; wi[1] = s1;
+#pragma unroll
+        for (int q = 2; q < 16; ++q) {
+          // w^q from the two closest already-known powers keeps the error at a few ulp
+          cmul(wr[q], wi[q], wr[q >> 1], wi[q >> 1], wr[q - (q >> 1)], wi[q - (q >> 1)]);
+        }
+        cis_cycles(16.0 * P.cps, w16r, w16i);
+      }
+      for (int g = g0; g < g1; ++g, ib += 16) {
+        uint4 q4 = *reinterpret_cast<const uint4*>(cur + 16 * g);
+        unsigned wq[4] = {q4.x, q4.y, q4.z, q4.w};
+        if (ib < 0 || ib + 16 > P.blk) {  // head / tail of the block: zero the foreign samples
+#pragma unroll
+          for (int b = 0; b < 16; ++b) {
+            int i = ib + b;
+            if (i < 0 || i >= P.blk) wq[b >> 2] &= ~(0xFFu << (8 * (b & 3)));
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) wq[j] ^= 0x80808080u;
+        const int kE = E.e - ib, kP = Pm.e - ib, kL = L.e - ib;
+        const int kb = min(min(kE, kP), min(kL, 16));
+        // tentative state after the event(s) at kb
+        CodeVar E2 = E, P2 = Pm, L2 = L;
+        if (kE == kb) E2.advance(P.inv_step, codeS);
+        if (kP == kb) P2.advance(P.inv_step, codeS);
+        if (kL == kb) L2.advance(P.inv_step, codeS);
+        const bool single = (E2.e - ib >= 16) && (P2.e - ib >= 16) && (L2.e - ib >= 16);
+        if (single) {
+          float Ar = 0.f, Ai = 0.f, Br = 0.f, Bi = 0.f;
+#pragma unroll
+          for (int b = 0; b < 16; ++b) {
+            float x = byte_to_float(wq[b >> 2], b & 3);
+            if (b < kb) { Ar = fmaf(x, wr[b], Ar); Ai = fmaf(x, wi[b], Ai); }
+            else        { Br = fmaf(x, wr[b], Br); Bi = fmaf(x, wi[b], Bi); }
+          }
+          float RAr, RAi, RBr, RBi;
+          cmul(RAr, RAi, rotr, roti, Ar, Ai);
+          cmul(RBr, RBi, rotr, roti, Br, Bi);
+          // group halves are float32 (<= 16 exact-int x float products each); totals run in float64
+          tEr += (double)(E.s * RAr + E2.s * RBr); tEi += (double)(E.s * RAi + E2.s * RBi);
+          tPr += (double)(Pm.s * RAr + P2.s * RBr); tPi += (double)(Pm.s * RAi + P2.s * RBi);
+          tLr += (double)(L.s * RAr + L2.s * RBr); tLi += (double)(L.s * RAi + L2.s * RBi);
+          E = E2; Pm = P2; L = L2;
+        } else {
+          // several chip boundaries inside one group (low sampling rates, or E/L boundaries that
+          // round to neighbouring samples): sample-by-sample walk
+          float rr = rotr, ri = roti;
+#pragma unroll
+          for (int b = 0; b < 16; ++b) {
+            const int i = ib + b;
+            while (E.e <= i) E.advance(P.inv_step, codeS);
+            while (Pm.e <= i) Pm.advance(P.inv_step, codeS);
+            while (L.e <= i) L.advance(P.inv_step, codeS);
+            float x = byte_to_float(wq[b >> 2], b & 3);
+            float pr = x * rr, pi = x * ri;
+            tEr += (double)(E.s * pr); tEi += (double)(E.s * pi);
+            tPr += (double)(Pm.s * pr); tPi += (double)(Pm.s * pi);
+            tLr += (double)(L.s * pr); tLi += (double)(L.s * pi);
+            float nr, ni;
+            cmul(nr, ni, rr, ri, wr[1], wi[1]);
+            rr = nr; ri = ni;
+          }
+          // bring the state to the first sample of the next group
+          while (E.e <= ib + 15) E.advance(P.inv_step, codeS);
+          while (Pm.e <= ib + 15) Pm.advance(P.inv_step, codeS);
+          while (L.e <= ib + 15) L.advance(P.inv_step, codeS);
+        }
+        float nr, ni;
+        cmul(nr, ni, rotr, roti, w16r, w16i);
+        rotr = nr; roti = ni;
+      }
+    }
+}
+
+// ---- correlate, variant B: every thread owns 8 half-chip segments --------------------------------
+// Threshold n (n = -1 .. 2046) is the value n/2 of the prompt code phase; beta(n) is the first sample
+// whose phase exceeds it: for even n the boundary of P (chip n/2), for odd n the common boundary of E
+// (chip (n-1)/2) and L (chip (n+1)/2).  Samples in [beta(n), beta(n+1)) therefore all have replica
+// indices P = floor(n/2)+1, E = floor((n+1)/2), L = E+1, so a segment is summed
+// without any per-sample decision: sum_k x[a+k] w^k with 4*NW fixed twiddles, bytes fetched with
+// unaligned 32-bit shared loads + funnel shifts, then one rotation and three signed accumulations.
+// If an E boundary and its L twin fall on different samples (phase within 1e-6 of a sample instant)
+// the thread falls back to the exact per-sample evaluation for its whole range.
+template <int NW>
+__device__ __forceinline__ void correlate_segments(const MsParams& P, const int8_t* cur, const float* codeS,
+                                                   int tid, double& tEr, double& tEi, double& tPr, double& tPi,
+                                                   double& tLr, double& tLi) {
+  constexpr int SEGS = 8;          // 2046 half chips / 256 threads
+  constexpr int LMAX = 4 * NW;     // longest segment the unrolled path takes
+  const int off = (int)(P.pos - (P.pos & ~15LL));
+  const int n0 = SEGS * tid - 1;
+  int beta[SEGS + 1];
+  bool irregular = false;
+#pragma unroll
+  for (int s = 0; s <= SEGS; ++s) {
+    const int n = n0 + s;
+    int b;
+    if (n < 0) b = 0;
+    else if (n > 2046) b = P.blk;
+    else if ((n & 1) == 0) b = next_event(n >> 1, P.startP, P.stepP, P.inv_step);
+    else {
+      const int c = (n - 1) >> 1;
+      const double q = ((double)c - P.startE) * P.inv_step;
+      const double fl = floor(q);
+      b = (int)fl + 1;
+      const double fr = q - fl;
+      if (fr < 1e-6 || fr > 1.0 - 1e-6) {   // too close to a sample instant: settle E and L exactly
+        b = next_event(c, P.startE, P.stepE, P.inv_step);
+        const int bl = next_event(c + 1, P.startL, P.stepL, P.inv_step);
+        if (bl != b) irregular = true;
+      }
+    }
+    beta[s] = min(b, P.blk);
+  }
+  if (beta[0] >= P.blk) return;
+  if (irregular) {
+    // exact per-sample evaluation of the three replica indices (tracking.py:166-188 verbatim)
+    for (int i = beta[0]; i < beta[SEGS]; ++i) {
+      const int ie = (int)ceil(lin_y(i, P.stepE, P.startE));
+      const int ip = (int)ceil(lin_y(i, P.stepP, P.startP));
+      const int il = (int)ceil(lin_y(i, P.stepL, P.startL));
+      float sn, cs;
+      cis_cycles((double)i * P.cps + P.rem_cyc, cs, sn);
+      const float x = (float)cur[off + i];
+      const float pr = x * cs, pi = x * sn;
+      tEr += (double)(codeS[ie] * pr); tEi += (double)(codeS[ie] * pi);
+      tPr += (double)(codeS[ip] * pr); tPi += (double)(codeS[ip] * pi);
+      tLr += (double)(codeS[il] * pr); tLi += (double)(codeS[il] * pi);
+    }
+    return;
+  }
+  // twiddles w^k, k = 0 .. LMAX-1 for the samples of a chunk, and the five rotor steps
+  // w^(LMAX-4) .. w^LMAX (segment lengths that occur), anchored on a freshly evaluated w^(LMAX-2)
+  float wr[LMAX], wi[LMAX], zr[5], zi[5];
+  {
+    float s1, c1;
+    cis_cycles(P.cps, c1, s1);
+    wr[0] = 1.f; wi[0] = 0.f;
+    if (LMAX > 1) { wr[1] = c1; wi[1] = s1; }
+#pragma unroll
+    for (int q = 2; q < LMAX; ++q)
+      cmul(wr[q], wi[q], wr[q >> 1], wi[q >> 1], wr[q - (q >> 1)], wi[q - (q >> 1)]);
+    cis_cycles((double)(LMAX - 2) * P.cps, zr[2], zi[2]);
+    float c2, s2;
+    cmul(c2, s2, c1, s1, c1, s1);
+    cmul(zr[3], zi[3], zr[2], zi[2], c1, s1);
+    cmul(zr[4], zi[4], zr[2], zi[2], c2, s2);
+    cmul(zr[1], zi[1], zr[2], zi[2], c1, -s1);
+    cmul(zr[0], zi[0], zr[2], zi[2], c2, -s2);
+  }
+  float rotr = 1.f, roti = 0.f;
+  bool fresh = true;
+#pragma unroll
+  for (int s = 0; s < SEGS; ++s) {
+    int a = beta[s];
+    const int b = beta[s + 1];
+    if (b <= a) continue;
+    const int n = n0 + s;
+    const float sP = codeS[(n >> 1) + 1];
+    const int ie = (n + 1) >> 1;
+    const float sE = codeS[ie], sL = codeS[ie + 1];
+    float Sr = 0.f, Si = 0.f;   // sum of this segment, referred to the carrier phase of sample `a0`
+    const int a0 = a;
+    if (fresh) {
+      cis_cycles((double)a * P.cps + P.rem_cyc, rotr, roti);
+      fresh = false;
+    }
+    float cr = 1.f, ci = 0.f;   // rotor of the current chunk relative to a0
+    while (a < b) {             // one chunk unless the segment is longer than LMAX (other sampling rates)
+      const int len = min(b - a, LMAX);
+      const int addr = off + a;
+      const unsigned* wp = reinterpret_cast<const unsigned*>(cur + (addr & ~3));
+      const int sh = (addr & 3) * 8;
+      unsigned raw[NW + 1];
+#pragma unroll
+      for (int q = 0; q <= NW; ++q) raw[q] = wp[q];
+      float pr = 0.f, pi = 0.f;
+#pragma unroll
+      for (int q = 0; q < NW; ++q) {
+        unsigned w = __funnelshift_r(raw[q], raw[q + 1], sh);
+        const int keep = len - 4 * q;                      // bytes of this word that belong to the chunk
+        if (keep < 4) w &= keep <= 0 ? 0u : (0xFFFFFFFFu >> (8 * (4 - keep)));
+        w ^= 0x80808080u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float x = byte_to_float(w, k);
+          pr = fmaf(x, wr[4 * q + k], pr);
+          pi = fmaf(x, wi[4 * q + k], pi);
+        }
+      }
+      float tr, ti;
+      cmul(tr, ti, cr, ci, pr, pi);
+      Sr += tr; Si += ti;
+      a += len;
+      if (a < b) {   // multi-chunk segment: advance the chunk rotor by w^LMAX
+        cmul(tr, ti, cr, ci, zr[4], zi[4]);
+        cr = tr; ci = ti;
+      }
+    }
+    float Rr, Ri;
+    cmul(Rr, Ri, rotr, roti, Sr, Si);
+    // a segment sum is float32 (<= 20 products of an exact int8 with a float twiddle); the running
+    // totals are float64 so that the six correlator outputs carry ~1e-8 relative error
+    const double dr = (double)Rr, di = (double)Ri;
+    tEr += (double)sE * dr; tEi += (double)sE * di;
+    tPr += (double)sP * dr; tPi += (double)sP * di;
+    tLr += (double)sL * dr; tLi += (double)sL * di;
+    // rotor for the next segment
+    const int len = b - a0;
+    const int j = len - (LMAX - 4);
+    if (j >= 0 && j <= 4) {
+      float sr = zr[0], si = zi[0];
+      if (j == 1) { sr = zr[1]; si = zi[1]; }
+      if (j == 2) { sr = zr[2]; si = zi[2]; }
+      if (j == 3) { sr = zr[3]; si = zi[3]; }
+      if (j == 4) { sr = zr[4]; si = zi[4]; }
+      float nr, ni;
+      cmul(nr, ni, rotr, roti, sr, si);
+      rotr = nr; roti = ni;
+    } else {
+      fresh = true;
+    }
+  }
+}
+
+template <bool BULK, int NW>
 __global__ void __launch_bounds__(TRK_THREADS, 2) track_kernel(TrackArgs a) {
   SGX_DYN_SMEM(smem);
   int8_t* buf0 = (int8_t*)smem;
   int8_t* buf1 = buf0 + a.win;
   __shared__ MsParams prm;
-  __shared__ float red[TRK_WARPS][6];
+  __shared__ double red[TRK_WARPS][6];
   __shared__ float codeS[1040];  // 1025 used; the tail absorbs indices reached only by masked samples
   __shared__ unsigned long long mbar[2];
 
@@ -237,111 +509,14 @@ __global__ void __launch_bounds__(TRK_THREADS, 2) track_kernel(TrackArgs a) {
       }
     }
 
-    // ---- correlate: contiguous run of 16-sample groups per thread --------------------------
-    const int off = (int)(P.pos - (P.pos & ~15LL));
-    const int ng = (off + P.blk + 15) >> 4;
-    const int gpt = (ng + TRK_THREADS - 1) / TRK_THREADS;
-    const int g0 = tid * gpt;
-    const int g1 = min(g0 + gpt, ng);
-    float tEr = 0.f, tEi = 0.f, tPr = 0.f, tPi = 0.f, tLr = 0.f, tLi = 0.f;
-    if (g0 < g1) {
-      int ib = 16 * g0 - off;
-      const int i0 = max(ib, 0);
-      CodeVar E, Pm, L;
-      E.init(i0, P.startE, P.stepE, P.inv_step, codeS);
-      Pm.init(i0, P.startP, P.stepP, P.inv_step, codeS);
-      L.init(i0, P.startL, P.stepL, P.inv_step, codeS);
-      // carrier: rot = e^{j theta(ib)}, w[k] = e^{j k dtheta}
-      float wr[16], wi[16], w16r, w16i, rotr, roti;
-      {
-        double ph = (double)ib * P.cps + P.rem_cyc;
-        ph -= rint(ph);
-        sincospif(2.0f * (float)ph, &roti, &rotr);
-        double d1 = P.cps - rint(P.cps);
-        float s1, c1;
-        sincospif(2.0f * (float)d1, &s1, &c1);
-        wr[0] = 1.f; wi[0] = 0.f; wr[1] = c1; wi[1] = s1;
-#pragma unroll
-        for (int q = 2; q < 16; ++q) {
-          // w^q from the two closest already-known powers keeps the error at a few ulp
-          cmul(wr[q], wi[q], wr[q >> 1], wi[q >> 1], wr[q - (q >> 1)], wi[q - (q >> 1)]);
-        }
-        double d16 = 16.0 * P.cps;
-        d16 -= rint(d16);
-        sincospif(2.0f * (float)d16, &w16i, &w16r);
-      }
-      for (int g = g0; g < g1; ++g, ib += 16) {
-        uint4 q4 = *reinterpret_cast<const uint4*>(cur + 16 * g);
-        unsigned wq[4] = {q4.x, q4.y, q4.z, q4.w};
-        if (ib < 0 || ib + 16 > P.blk) {  // head / tail of the block: zero the foreign samples
-#pragma unroll
-          for (int b = 0; b < 16; ++b) {
-            int i = ib + b;
-            if (i < 0 || i >= P.blk) wq[b >> 2] &= ~(0xFFu << (8 * (b & 3)));
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) wq[j] ^= 0x80808080u;
-        const int kE = E.e - ib, kP = Pm.e - ib, kL = L.e - ib;
-        const int kb = min(min(kE, kP), min(kL, 16));
-        // tentative state after the event(s) at kb
-        CodeVar E2 = E, P2 = Pm, L2 = L;
-        if (kE == kb) E2.advance(P.inv_step, codeS);
-        if (kP == kb) P2.advance(P.inv_step, codeS);
-        if (kL == kb) L2.advance(P.inv_step, codeS);
-        const bool single = (E2.e - ib >= 16) && (P2.e - ib >= 16) && (L2.e - ib >= 16);
-        if (single) {
-          float Ar = 0.f, Ai = 0.f, Br = 0.f, Bi = 0.f;
-#pragma unroll
-          for (int b = 0; b < 16; ++b) {
-            float x = byte_to_float(wq[b >> 2], b & 3);
-            if (b < kb) { Ar = fmaf(x, wr[b], Ar); Ai = fmaf(x, wi[b], Ai); }
-            else        { Br = fmaf(x, wr[b], Br); Bi = fmaf(x, wi[b], Bi); }
-          }
-          float RAr, RAi, RBr, RBi;
-          cmul(RAr, RAi, rotr, roti, Ar, Ai);
-          cmul(RBr, RBi, rotr, roti, Br, Bi);
-          tEr = fmaf(E.s, RAr, tEr); tEi = fmaf(E.s, RAi, tEi);
-          tPr = fmaf(Pm.s, RAr, tPr); tPi = fmaf(Pm.s, RAi, tPi);
-          tLr = fmaf(L.s, RAr, tLr); tLi = fmaf(L.s, RAi, tLi);
-          tEr = fmaf(E2.s, RBr, tEr); tEi = fmaf(E2.s, RBi, tEi);
-          tPr = fmaf(P2.s, RBr, tPr); tPi = fmaf(P2.s, RBi, tPi);
-          tLr = fmaf(L2.s, RBr, tLr); tLi = fmaf(L2.s, RBi, tLi);
-          E = E2; Pm = P2; L = L2;
-        } else {
-          // several chip boundaries inside one group (low sampling rates, or E/L boundaries that
-          // round to neighbouring samples): sample-by-sample walk
-          float rr = rotr, ri = roti;
-#pragma unroll
-          for (int b = 0; b < 16; ++b) {
-            const int i = ib + b;
-            while (E.e <= i) E.advance(P.inv_step, codeS);
-            while (Pm.e <= i) Pm.advance(P.inv_step, codeS);
-            while (L.e <= i) L.advance(P.inv_step, codeS);
-            float x = byte_to_float(wq[b >> 2], b & 3);
-            float pr = x * rr, pi = x * ri;
-            tEr = fmaf(E.s, pr, tEr); tEi = fmaf(E.s, pi, tEi);
-            tPr = fmaf(Pm.s, pr, tPr); tPi = fmaf(Pm.s, pi, tPi);
-            tLr = fmaf(L.s, pr, tLr); tLi = fmaf(L.s, pi, tLi);
-            float nr, ni;
-            cmul(nr, ni, rr, ri, wr[1], wi[1]);
-            rr = nr; ri = ni;
-          }
-          // bring the state to the first sample of the next group
-          while (E.e <= ib + 15) E.advance(P.inv_step, codeS);
-          while (Pm.e <= ib + 15) Pm.advance(P.inv_step, codeS);
-          while (L.e <= ib + 15) L.advance(P.inv_step, codeS);
-        }
-        float nr, ni;
-        cmul(nr, ni, rotr, roti, w16r, w16i);
-        rotr = nr; roti = ni;
-      }
-    }
+    double tEr = 0.0, tEi = 0.0, tPr = 0.0, tPi = 0.0, tLr = 0.0, tLi = 0.0;
+    if (NW > 0) correlate_segments<(NW > 0 ? NW : 1)>(P, cur, codeS, tid, tEr, tEi, tPr, tPi, tLr, tLi);
+    else        correlate_groups(P, cur, codeS, tid, tEr, tEi, tPr, tPi, tLr, tLi);
     // I arm = sin (imaginary part), Q arm = cos (real part): tracking.py:205-207
-    float v0 = warp_sum(tEi), v1 = warp_sum(tEr), v2 = warp_sum(tPi), v3 = warp_sum(tPr),
-          v4 = warp_sum(tLi), v5 = warp_sum(tLr);
+    double v0 = warp_sum_f64(tEi), v1 = warp_sum_f64(tEr), v2 = warp_sum_f64(tPi), v3 = warp_sum_f64(tPr),
+           v4 = warp_sum_f64(tLi), v5 = warp_sum_f64(tLr);
     if ((tid & 31) == 0) {
-      float* r = red[tid >> 5];
+      double* r = red[tid >> 5];
       r[0] = v0; r[1] = v1; r[2] = v2; r[3] = v3; r[4] = v4; r[5] = v5;
     }
     if (!BULK) cp_async_wait_all();
@@ -351,7 +526,7 @@ __global__ void __launch_bounds__(TRK_THREADS, 2) track_kernel(TrackArgs a) {
 #pragma unroll
       for (int j = 0; j < 6; ++j) {
         double acc = 0.0;
-        for (int w = 0; w < TRK_WARPS; ++w) acc += (double)red[w][j];
+        for (int w = 0; w < TRK_WARPS; ++w) acc += red[w][j];
         s[j] = acc;
       }
       const double I_E = s[0], Q_E = s[1], I_P = s[2], Q_P = s[3], I_L = s[4], Q_L = s[5];
@@ -359,7 +534,7 @@ __global__ void __launch_bounds__(TRK_THREADS, 2) track_kernel(TrackArgs a) {
       st.remCarrPhase = nextRemCarr;
       st.pos = P.pos + P.blk;
       // PLL (tracking.py:223-235)
-      double carrError = atan(Q_P / I_P) / 2.0 / 3.141592653589793;
+      double carrError = atan(Q_P / I_P) * 0.5 / 3.141592653589793;   // x/2.0 == x*0.5 exactly
       double carrNco = st.oldCarrNco + a.c1carr * (carrError - st.oldCarrError) + carrError * a.c2carr;
       st.oldCarrNco = carrNco;
       st.oldCarrError = carrError;
@@ -478,15 +653,28 @@ extern "C" int sgx_track(const int8_t* rec, int64_t rec_stride, const int64_t* r
   a.c2carr = st->PDIcarr / st->tau1carr;
 
   const size_t smem = 2 * (size_t)win;
-  if (use_bulk()) {
-    auto kfn = track_kernel<true>;
-    SGX_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SGX_COUNTED_LAUNCH(kfn, dim3(nch), dim3(TRK_THREADS), smem, s, a);
-  } else {
-    auto kfn = track_kernel<false>;
-    SGX_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SGX_COUNTED_LAUNCH(kfn, dim3(nch), dim3(TRK_THREADS), smem, s, a);
+  // correlate variant: half-chip segments when a segment fits the unrolled path, else aligned groups
+  const double half_chip = st->samplingFreq / (2.0 * st->codeFreqBasis);   // samples per half chip
+  int nw = ((int)ceil(half_chip + 0.25) + 3) / 4;
+  if (const char* e = getenv("SGX_TRK_KERNEL")) { if (strcmp(e, "groups") == 0) nw = 0; }
+  if (fabs(st->dllCorrelatorSpacing - 0.5) > 1e-12) nw = 0;                 // segment scheme assumes E/L at +-0.5 chip
+  const bool bulk = use_bulk();
+#define SGX_TRK_GO(B, W)                                                                           \
+  {                                                                                                \
+    auto kfn = track_kernel<B, W>;                                                                 \
+    SGX_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    SGX_COUNTED_LAUNCH(kfn, dim3(nch), dim3(TRK_THREADS), smem, s, a);                             \
   }
+#define SGX_TRK_PICK(W) { if (bulk) SGX_TRK_GO(true, W) else SGX_TRK_GO(false, W) }
+  switch (nw) {
+    case 2: SGX_TRK_PICK(2) break;
+    case 4: SGX_TRK_PICK(4) break;
+    case 5: SGX_TRK_PICK(5) break;
+    case 8: SGX_TRK_PICK(8) break;
+    default: SGX_TRK_PICK(0) break;
+  }
+#undef SGX_TRK_PICK
+#undef SGX_TRK_GO
   SGX_CUDA(cudaGetLastError());
   if (out_on_host) SGX_CUDA(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, s));
   int* h_status = (int*)malloc(sizeof(int) * nch);

@@ -40,11 +40,15 @@ def test_synth_device_bit_identical(native, recordings):
         assert not out[0, n:].any()
 
 
+@pytest.mark.parametrize("variant", ["segments", "groups"])
 @pytest.mark.parametrize("stage", ["bulk", "cpasync"])
 @pytest.mark.parametrize("name", ["trk_small", "trk_skip"])
-def test_tracking_matches_reference_golden(native, recordings, name, stage, monkeypatch):
+def test_tracking_matches_reference_golden(native, recordings, name, stage, variant, monkeypatch):
+    """Both staging paths (TMA bulk copy / cp.async) and both correlator formulations (half-chip
+    segments / aligned 16-sample groups) against the reference's own output."""
     from softgnss_python_b200.tracking import tracking
     monkeypatch.setenv("SGX_TRK_STAGE", stage)
+    monkeypatch.setenv("SGX_TRK_KERNEL", variant)
     g = gold(name)
     _, data = recordings[name]
     s = case_settings(CASES[name])

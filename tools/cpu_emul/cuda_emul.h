@@ -288,6 +288,9 @@ static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned s) {
   }
   return r;
 }
+static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) {
+  return (unsigned)(((((unsigned long long)hi) << 32) | lo) >> (sh & 31));
+}
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
 static inline int __ffs(int x) { return __builtin_ffs(x); }

@@ -12,7 +12,7 @@ from softgnss_python_b200 import _native, synth            # noqa: E402
 from softgnss_python_b200.settings import to_pod            # noqa: E402
 from tests.cases import CASES, N, build_recording, case_settings   # noqa: E402
 
-L = _native.Lib(os.path.join(ROOT, "tools", "cpu_emul", "libsoftgnss_emul.so"))
+L = _native.Lib(os.environ.get("SGX_EMUL_LIB", os.path.join(ROOT, "tools", "cpu_emul", "libsoftgnss_emul.so")))
 
 
 def check_synth():
@@ -56,3 +56,37 @@ def check_track(name, ms=None):
 if __name__ == "__main__":
     check_synth()
     check_track("trk_small", ms=int(sys.argv[1]) if len(sys.argv) > 1 else 40)
+
+
+def dump(name, ms):
+    case = CASES[name]
+    g = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    spec, data = build_recording(case)
+    s = case_settings(case)
+    s.msToProcess = ms
+    pod = to_pod(s)
+    chans = _native.make_channels(g["ch_PRN"], g["ch_acquiredFreq"], g["ch_codePhase"])
+    c = len(g["ch_PRN"])
+    out = np.zeros((1, c, 13, pod.msToProcess))
+    rc, done = L.track(data.reshape(1, -1), data.size, [data.size], chans, pod, _native.ca_chips_int8(), out)
+    for ch in range(c):
+        for k in range(ms):
+            print(ch, k, "I_P", out[0, ch, 3, k], g["trk_I_P"][ch, k], "Q_P", out[0, ch, 7, k], g["trk_Q_P"][ch, k],
+                  "I_E", out[0, ch, 4, k], g["trk_I_E"][ch, k])
+
+
+def worst(name, ms):
+    case = CASES[name]
+    g = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    spec, data = build_recording(case)
+    s = case_settings(case)
+    s.msToProcess = ms
+    pod = to_pod(s)
+    chans = _native.make_channels(g["ch_PRN"], g["ch_acquiredFreq"], g["ch_codePhase"])
+    c = len(g["ch_PRN"])
+    out = np.zeros((1, c, 13, pod.msToProcess))
+    rc, done = L.track(data.reshape(1, -1), data.size, [data.size], chans, pod, _native.ca_chips_int8(), out)
+    d = np.abs(out[0, :, 3, :] - g["trk_I_P"][:, :ms])
+    for ch in range(c):
+        k = np.argsort(-d[ch])[:5]
+        print(ch, [(int(x), float(d[ch, x])) for x in k])
