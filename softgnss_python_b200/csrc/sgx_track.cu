@@ -61,13 +61,6 @@ struct MsParams {
   int stop;         // 0 = run this period, else sgx_status / 1 = finished
 };
 
-// thread-0 loop state (tracking.py:114-130)
-struct LoopState {
-  double codeFreq, remCodePhase, carrFreq, carrFreqBasis, remCarrPhase;
-  double oldCodeNco, oldCodeError, oldCarrNco, oldCarrError;
-  long long pos;
-};
-
 __device__ __forceinline__ double lin_y(int i, double step, double start) {
   // element i of np.linspace: two roundings, multiply then add (no FMA)
   return __dadd_rn(__dmul_rn((double)i, step), start);
@@ -130,11 +123,19 @@ __device__ __forceinline__ void cmul(float& r, float& i, float ar, float ai, flo
   i = fmaf(ar, bi, ai * br);
 }
 
-// T3 + T4 parameters + T5/T6 carries for the next period, evaluated by thread 0 in float64.
-__device__ void prepare_period(const TrackArgs& a, LoopState& st, long long rec_len, MsParams& p,
-                               double& nextRemCode, double& nextRemCarr) {
-  const double TWO_PI = 6.283185307179586;  // == 2*np.pi
-  const double PI = 3.141592653589793;
+// The per-period float64 bookkeeping is split over two threads of different warps so that the two
+// dependent chains run concurrently: thread 0 owns the code loop (T3, T4 parameters, T5, T9), thread 32
+// the carrier loop (T6, T8).  Neither needs the other's result within a period.
+struct CodeState {   // tracking.py:114-116, :124-126
+  double codeFreq, remCodePhase, oldCodeNco, oldCodeError, nextRemCode;
+  long long pos;
+};
+struct CarrState {   // tracking.py:118-122, :128-130
+  double carrFreq, carrFreqBasis, remCarrPhase, oldCarrNco, oldCarrError, w;
+};
+
+// T3 + T4 parameters + T5 carry for the next period (code thread)
+__device__ void prepare_code(const TrackArgs& a, CodeState& st, long long rec_len, MsParams& p) {
   double step = st.codeFreq / a.fs;                                   // :148
   int blk = (int)ceil((a.codeLength - st.remCodePhase) / step);       // :150
   p.blk = blk;
@@ -151,10 +152,21 @@ __device__ void prepare_period(const TrackArgs& a, LoopState& st, long long rec_
   p.startP = rem;                                                     // :182
   p.stepP = ((bs + rem) - p.startP) / (double)blk;
   p.inv_step = 1.0 / step;
-  nextRemCode = (lin_y(blk - 1, p.stepP, p.startP) + step) - 1023.0;  // :190
-  double w = st.carrFreq * 2.0 * PI;                                  // :195
-  double arg_end = w * ((double)blk / a.fs) + st.remCarrPhase;
-  double m;                                                           // :197 (np.remainder)
+  st.nextRemCode = (lin_y(blk - 1, p.stepP, p.startP) + step) - 1023.0;  // :190
+}
+
+// T6: carrier NCO parameters of the next period (carrier thread)
+__device__ void prepare_carr(const TrackArgs& a, CarrState& st, MsParams& p) {
+  st.w = st.carrFreq * 2.0 * 3.141592653589793;                       // :195
+  p.cps = (st.w / a.fs) * 0.15915494309189535;
+  p.rem_cyc = st.remCarrPhase * 0.15915494309189535;
+}
+
+// T6 carry (tracking.py:197): remCarrPhase after a block of `blk` samples
+__device__ double carry_carr_phase(const TrackArgs& a, const CarrState& st, int blk) {
+  const double TWO_PI = 6.283185307179586;  // == 2*np.pi
+  double arg_end = st.w * ((double)blk / a.fs) + st.remCarrPhase;
+  double m;
   if (arg_end >= 0.0) {
     // exact remainder without the iterative fmod: with the right integer quotient the fused
     // multiply-add returns x - q*y exactly (the result of fmod is always representable)
@@ -166,9 +178,7 @@ __device__ void prepare_period(const TrackArgs& a, LoopState& st, long long rec_
     m = fmod(arg_end, TWO_PI);
     if (m != 0.0 && m < 0.0) m += TWO_PI;
   }
-  nextRemCarr = m;
-  p.cps = (w / a.fs) * 0.15915494309189535;
-  p.rem_cyc = st.remCarrPhase * 0.15915494309189535;
+  return m;
 }
 
 // ---- correlate, variant A: contiguous run of aligned 16-sample groups per thread (any sampling rate)
@@ -345,6 +355,7 @@ __device__ __forceinline__ void correlate_segments(const MsParams& P, const int8
     cmul(zr[0], zi[0], zr[2], zi[2], c2, -s2);
   }
   float rotr = 1.f, roti = 0.f;
+  float fEr = 0.f, fEi = 0.f, fPr = 0.f, fPi = 0.f, fLr = 0.f, fLi = 0.f;
   bool fresh = true;
 #pragma unroll
   for (int s = 0; s < SEGS; ++s) {
@@ -362,6 +373,7 @@ __device__ __forceinline__ void correlate_segments(const MsParams& P, const int8
       fresh = false;
     }
     float cr = 1.f, ci = 0.f;   // rotor of the current chunk relative to a0
+    bool first_chunk = true;
     while (a < b) {             // one chunk unless the segment is longer than LMAX (other sampling rates)
       const int len = min(b - a, LMAX);
       const int addr = off + a;
@@ -370,13 +382,22 @@ __device__ __forceinline__ void correlate_segments(const MsParams& P, const int8
       unsigned raw[NW + 1];
 #pragma unroll
       for (int q = 0; q <= NW; ++q) raw[q] = wp[q];
+      unsigned wq[NW];
+#pragma unroll
+      for (int q = 0; q < NW; ++q) wq[q] = __funnelshift_r(raw[q], raw[q + 1], sh);
+      if (len > LMAX - 4) {     // the usual case: only the last word is partial
+        wq[NW - 1] &= 0xFFFFFFFFu >> (8 * (LMAX - len));
+      } else {
+#pragma unroll
+        for (int q = 0; q < NW; ++q) {
+          const int keep = len - 4 * q;
+          if (keep < 4) wq[q] &= keep <= 0 ? 0u : (0xFFFFFFFFu >> (8 * (4 - keep)));
+        }
+      }
       float pr = 0.f, pi = 0.f;
 #pragma unroll
       for (int q = 0; q < NW; ++q) {
-        unsigned w = __funnelshift_r(raw[q], raw[q + 1], sh);
-        const int keep = len - 4 * q;                      // bytes of this word that belong to the chunk
-        if (keep < 4) w &= keep <= 0 ? 0u : (0xFFFFFFFFu >> (8 * (4 - keep)));
-        w ^= 0x80808080u;
+        const unsigned w = wq[q] ^ 0x80808080u;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const float x = byte_to_float(w, k);
@@ -384,23 +405,28 @@ __device__ __forceinline__ void correlate_segments(const MsParams& P, const int8
           pi = fmaf(x, wi[4 * q + k], pi);
         }
       }
-      float tr, ti;
-      cmul(tr, ti, cr, ci, pr, pi);
-      Sr += tr; Si += ti;
       a += len;
+      if (first_chunk) {
+        Sr = pr; Si = pi;
+        first_chunk = false;
+      } else {
+        float tr, ti;
+        cmul(tr, ti, cr, ci, pr, pi);
+        Sr += tr; Si += ti;
+      }
       if (a < b) {   // multi-chunk segment: advance the chunk rotor by w^LMAX
+        float tr, ti;
         cmul(tr, ti, cr, ci, zr[4], zi[4]);
         cr = tr; ci = ti;
       }
     }
     float Rr, Ri;
     cmul(Rr, Ri, rotr, roti, Sr, Si);
-    // a segment sum is float32 (<= 20 products of an exact int8 with a float twiddle); the running
-    // totals are float64 so that the six correlator outputs carry ~1e-8 relative error
-    const double dr = (double)Rr, di = (double)Ri;
-    tEr += (double)sE * dr; tEi += (double)sE * di;
-    tPr += (double)sP * dr; tPi += (double)sP * di;
-    tLr += (double)sL * dr; tLi += (double)sL * di;
+    // eight segment sums per thread stay float32 (rounding 6e-8 of a 1/256 share of the total,
+    // independent between threads); everything across threads is added in float64
+    fEr = fmaf(sE, Rr, fEr); fEi = fmaf(sE, Ri, fEi);
+    fPr = fmaf(sP, Rr, fPr); fPi = fmaf(sP, Ri, fPi);
+    fLr = fmaf(sL, Rr, fLr); fLi = fmaf(sL, Ri, fLi);
     // rotor for the next segment
     const int len = b - a0;
     const int j = len - (LMAX - 4);
@@ -417,6 +443,7 @@ __device__ __forceinline__ void correlate_segments(const MsParams& P, const int8
       fresh = true;
     }
   }
+  tEr += (double)fEr; tEi += (double)fEi; tPr += (double)fPr; tPi += (double)fPi; tLr += (double)fLr; tLi += (double)fLi;
 }
 
 template <bool BULK, int NW>
@@ -444,18 +471,22 @@ __global__ void __launch_bounds__(TRK_THREADS, 2) track_kernel(TrackArgs a) {
     const int8_t* c = a.chips + (chn.prn - 1) * 1023;
     for (int i = tid; i < 1040; i += TRK_THREADS) codeS[i] = i < 1025 ? (float)c[(i + 1022) % 1023] : 0.f;
   }
-  LoopState st;
-  double nextRemCode = 0.0, nextRemCarr = 0.0;
+  CodeState cst;
+  CarrState rst;
   if (tid == 0) {
-    st.codeFreq = a.codeFreqBasis;          // :114
-    st.remCodePhase = 0.0;
-    st.carrFreq = chn.acquiredFreq;         // :118
-    st.carrFreqBasis = chn.acquiredFreq;
-    st.remCarrPhase = 0.0;
-    st.oldCodeNco = st.oldCodeError = st.oldCarrNco = st.oldCarrError = 0.0;
-    st.pos = a.skip + (long long)chn.codePhase;  // :107
-    prepare_period(a, st, rec_len, prm, nextRemCode, nextRemCarr);
+    cst.codeFreq = a.codeFreqBasis;          // :114
+    cst.remCodePhase = 0.0;
+    cst.oldCodeNco = cst.oldCodeError = 0.0;
+    cst.pos = a.skip + (long long)chn.codePhase;  // :107
+    prepare_code(a, cst, rec_len, prm);
     if (BULK) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); }
+  }
+  if (tid == 32) {
+    rst.carrFreq = chn.acquiredFreq;         // :118
+    rst.carrFreqBasis = chn.acquiredFreq;
+    rst.remCarrPhase = 0.0;
+    rst.oldCarrNco = rst.oldCarrError = 0.0;
+    prepare_carr(a, rst, prm);
   }
   __syncthreads();
 
@@ -521,41 +552,39 @@ __global__ void __launch_bounds__(TRK_THREADS, 2) track_kernel(TrackArgs a) {
     }
     if (!BULK) cp_async_wait_all();
     __syncthreads();
-    if (tid == 0) {
-      double s[6];
-#pragma unroll
-      for (int j = 0; j < 6; ++j) {
-        double acc = 0.0;
-        for (int w = 0; w < TRK_WARPS; ++w) acc += red[w][j];
-        s[j] = acc;
-      }
-      const double I_E = s[0], Q_E = s[1], I_P = s[2], Q_P = s[3], I_L = s[4], Q_L = s[5];
-      st.remCodePhase = nextRemCode;
-      st.remCarrPhase = nextRemCarr;
-      st.pos = P.pos + P.blk;
-      // PLL (tracking.py:223-235)
-      double carrError = atan(Q_P / I_P) * 0.5 / 3.141592653589793;   // x/2.0 == x*0.5 exactly
-      double carrNco = st.oldCarrNco + a.c1carr * (carrError - st.oldCarrError) + carrError * a.c2carr;
-      st.oldCarrNco = carrNco;
-      st.oldCarrError = carrError;
-      st.carrFreq = st.carrFreqBasis + carrNco;
-      // DLL (tracking.py:238-251)
+    if (tid == 0) {          // ---- code thread: DLL (tracking.py:238-251), T5, T3/T4 of the next period
+      double I_E = 0.0, Q_E = 0.0, I_L = 0.0, Q_L = 0.0;
+      for (int w = 0; w < TRK_WARPS; ++w) { I_E += red[w][0]; Q_E += red[w][1]; I_L += red[w][4]; Q_L += red[w][5]; }
+      cst.remCodePhase = cst.nextRemCode;
+      cst.pos = P.pos + P.blk;
       double em = sqrt(I_E * I_E + Q_E * Q_E), lm = sqrt(I_L * I_L + Q_L * Q_L);
       double codeError = (em - lm) / (em + lm);
-      double codeNco = st.oldCodeNco + a.c1code * (codeError - st.oldCodeError) + codeError * a.c2code;
-      st.oldCodeNco = codeNco;
-      st.oldCodeError = codeError;
-      st.codeFreq = a.codeFreqBasis - codeNco;
-      // record (tracking.py:255-275)
+      double codeNco = cst.oldCodeNco + a.c1code * (codeError - cst.oldCodeError) + codeError * a.c2code;
+      cst.oldCodeNco = codeNco;
+      cst.oldCodeError = codeError;
+      cst.codeFreq = a.codeFreqBasis - codeNco;
+      if (k + 1 < a.ms) prepare_code(a, cst, rec_len, prm);
+      double* o = a.out + (long long)cid * SGX_TRACK_FIELDS * a.ms + k;   // record (tracking.py:255-275)
+      const long long m = a.ms;
+      o[0 * m] = (double)cst.pos;  // fid.tell() after the read
+      o[1 * m] = cst.codeFreq;
+      o[4 * m] = I_E; o[5 * m] = I_L; o[6 * m] = Q_E; o[8 * m] = Q_L;
+      o[9 * m] = codeError; o[10 * m] = codeNco;
+    } else if (tid == 32) {  // ---- carrier thread: T6 carry, PLL (tracking.py:223-235), T6 of the next period
+      double I_P = 0.0, Q_P = 0.0;
+      for (int w = 0; w < TRK_WARPS; ++w) { I_P += red[w][2]; Q_P += red[w][3]; }
+      rst.remCarrPhase = carry_carr_phase(a, rst, P.blk);
+      double carrError = atan(Q_P / I_P) * 0.5 / 3.141592653589793;   // x/2.0 == x*0.5 exactly
+      double carrNco = rst.oldCarrNco + a.c1carr * (carrError - rst.oldCarrError) + carrError * a.c2carr;
+      rst.oldCarrNco = carrNco;
+      rst.oldCarrError = carrError;
+      rst.carrFreq = rst.carrFreqBasis + carrNco;
+      if (k + 1 < a.ms) prepare_carr(a, rst, prm);
       double* o = a.out + (long long)cid * SGX_TRACK_FIELDS * a.ms + k;
       const long long m = a.ms;
-      o[0 * m] = (double)st.pos;  // fid.tell() after the read
-      o[1 * m] = st.codeFreq;
-      o[2 * m] = st.carrFreq;
-      o[3 * m] = I_P; o[4 * m] = I_E; o[5 * m] = I_L;
-      o[6 * m] = Q_E; o[7 * m] = Q_P; o[8 * m] = Q_L;
-      o[9 * m] = codeError; o[10 * m] = codeNco; o[11 * m] = carrError; o[12 * m] = carrNco;
-      if (k + 1 < a.ms) prepare_period(a, st, rec_len, prm, nextRemCode, nextRemCarr);
+      o[2 * m] = rst.carrFreq;
+      o[3 * m] = I_P; o[7 * m] = Q_P;
+      o[11 * m] = carrError; o[12 * m] = carrNco;
     }
     __syncthreads();
   }
