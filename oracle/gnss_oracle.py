@@ -133,11 +133,13 @@ def acquire(long_signal, s, coherent_ms=1, noncoh_blocks=2, doppler_step=500.0,
             spec[b, k] = np.fft.fft(sin_c * blocks[b] + 1j * (cos_c * blocks[b]))  # :107-117
     for prn in range(nprn):
         code_f = np.fft.fft(table[prn]).conj()                             # :95
-        results = np.zeros((nbins, n))
+        results = np.zeros((nbins, n1))
         for k in range(nbins):
             best = None
             for b in range(noncoh_blocks):
                 r = abs(np.fft.ifft(spec[b, k] * code_f)) ** 2             # :120-126
+                if coherent_ms > 1:
+                    r = r[:n1]      # extension: the correlation repeats every code period; search one
                 # :129-133 keep block 1 only if strictly larger, later blocks win ties
                 if best is None or not (best.max() > r.max()):
                     best = r
@@ -146,9 +148,9 @@ def acquire(long_signal, s, coherent_ms=1, noncoh_blocks=2, doppler_step=500.0,
         peak = results.max(0).max()                                        # :142
         cp = int(results.max(0).argmax())                                  # :143
         chip = int(round(s.samplingFreq / s.codeFreqBasis))                # :145
-        rng = _exclusion_range(cp, chip, n)
+        rng = _exclusion_range(cp, chip, n1)
         if clamp_window:
-            rng = rng[rng < n]
+            rng = rng[rng < n1]
         second = results[fbin, rng].max()                                  # :162
         metric[prn] = peak / second                                        # :164
         if return_debug:

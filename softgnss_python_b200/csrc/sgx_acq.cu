@@ -126,8 +126,10 @@ struct EpiPeak {  // |.|^2 and arg-max of the whole row; one key per (item, tile
   int ntiles;
   long long item0;
   unsigned long long best;
+  int n1;   // code phases searched: one code period (the correlation repeats with period n1 when coherent ms > 1)
   __device__ __forceinline__ void begin(int) { best = 0ull; }
   __device__ __forceinline__ void put(int i, cpx v) {
+    if (i >= n1) return;
     const float mag = fmaf(v.x, v.x, v.y * v.y);
     const unsigned long long k = fft::peak_key(mag, (unsigned)i);
     best = k > best ? k : best;
@@ -157,7 +159,7 @@ struct EpiSecond {  // arg-max over the candidates only
   int cp;
   __device__ __forceinline__ void begin(int batch) { best = 0ull; cp = sel[batch].codePhase; }
   __device__ __forceinline__ void put(int i, cpx v) {
-    if (!second_peak_candidate(i, cp, chip, n)) return;
+    if (i >= n || !second_peak_candidate(i, cp, chip, n)) return;
     const float mag = fmaf(v.x, v.x, v.y * v.y);
     const unsigned long long k = fft::peak_key(mag, (unsigned)i);
     best = k > best ? k : best;
@@ -432,7 +434,7 @@ extern "C" int sgx_acquire(const int8_t* sig, int64_t rec_stride, int64_t n_samp
   for (long long i0 = 0; i0 < nitems; i0 += chunk) {
     const int cnt = (int)((nitems - i0) < chunk ? (nitems - i0) : chunk);
     EpiPeak ep;
-    ep.partial = a.partial.as<unsigned long long>(); ep.ntiles = nt_last; ep.item0 = i0; ep.best = 0;
+    ep.partial = a.partial.as<unsigned long long>(); ep.ntiles = nt_last; ep.item0 = i0; ep.best = 0; ep.n1 = n1;
     rc = run_fft(a.inv, true, cnt, ProMul{a.spec.as<cpx>(), a.codeF.as<cpx>(), d, (int)n, i0}, ep, a.work0.as<cpx>(),
                  a.work1.as<cpx>(), s);
     if (rc) return rc;
@@ -443,7 +445,7 @@ extern "C" int sgx_acquire(const int8_t* sig, int64_t rec_stride, int64_t n_samp
   {
     EpiSecond es;
     es.partial = a.partial2.as<unsigned long long>(); es.sel = a.sel.as<PeakSel>(); es.ntiles = nt_last;
-    es.chip = st->samplesPerCodeChip; es.n = (int)n; es.best = 0; es.cp = 0;
+    es.chip = st->samplesPerCodeChip; es.n = n1; es.best = 0; es.cp = 0;   // candidates within one code period
     rc = run_fft(a.inv, true, npr, ProMulSel{a.spec.as<cpx>(), a.codeF.as<cpx>(), a.sel.as<PeakSel>(), d, (int)n}, es,
                  a.work0.as<cpx>(), a.work1.as<cpx>(), s);
     if (rc) return rc;
