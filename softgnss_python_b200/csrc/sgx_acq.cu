@@ -94,6 +94,37 @@ struct ProMulSel {  // same product for the winning (bin, block) of PRN item (re
   __device__ __forceinline__ cpx load(int i) const { return fft::cmulf(spec[i], codeF[i]); }
 };
 
+struct SrcMul {  // async variant of ProMul: streamed = spectrum, second operand = code spectrum of the PRN
+  const cpx* spec;
+  const cpx* codeF;
+  SearchDims d;
+  int n;
+  long long item0;
+  __device__ __forceinline__ void locate(int batch, const cpx*& src, const cpx*& aux) const {
+    long long item = item0 + batch;
+    const int blk = (int)(item % d.blocks); item /= d.blocks;
+    const int bin = (int)(item % d.nbins); item /= d.nbins;
+    const int prn = (int)(item % d.nprn);
+    const int rec = (int)(item / d.nprn);
+    src = spec + (((long long)rec * d.blocks + blk) * d.nbins + bin) * n;
+    aux = codeF + (long long)(d.prn_first + prn) * n;
+  }
+};
+
+struct SrcMulSel {  // async variant of ProMulSel
+  const cpx* spec;
+  const cpx* codeF;
+  const PeakSel* sel;
+  SearchDims d;
+  int n;
+  __device__ __forceinline__ void locate(int batch, const cpx*& src, const cpx*& aux) const {
+    const PeakSel s = sel[batch];
+    const int prn = batch % d.nprn, rec = batch / d.nprn;
+    src = spec + (((long long)rec * d.blocks + s.blk) * d.nbins + s.bin) * n;
+    aux = codeF + (long long)(d.prn_first + prn) * n;
+  }
+};
+
 struct FineItem {
   int rec, prn, codePhase, pad;
 };
@@ -287,14 +318,94 @@ static int run_fft(const fft::Plan& pl, bool inverse, int batch, Pro pro, Epi ep
   if (pl.npass == 1) return launch_pass(pl, 0, inverse, batch, pro, epi, s);
   cpx* cur = w0;
   cpx* oth = w1;
-  int rc = launch_pass(pl, 0, inverse, batch, pro, fft::StoreCpx{cur, n, 1.f, 0}, s);
+  int rc = launch_pass(pl, 0, inverse, batch, pro, fft::StoreCpx{cur, n, 1.f, 0, nullptr}, s);
   if (rc) return rc;
   for (int p = 1; p + 1 < pl.npass; ++p) {
-    rc = launch_pass(pl, p, inverse, batch, fft::LoadCpx{cur, n}, fft::StoreCpx{oth, n, 1.f, 0}, s);
+    rc = launch_pass(pl, p, inverse, batch, fft::LoadCpx{cur, n, nullptr}, fft::StoreCpx{oth, n, 1.f, 0, nullptr}, s);
     if (rc) return rc;
     cpx* t = cur; cur = oth; oth = t;
   }
-  return launch_pass(pl, pl.npass - 1, inverse, batch, fft::LoadCpx{cur, n}, epi, s);
+  return launch_pass(pl, pl.npass - 1, inverse, batch, fft::LoadCpx{cur, n, nullptr}, epi, s);
+}
+
+static bool use_async() {
+  const char* e = getenv("SGX_ACQ_ASYNC");
+  return !(e && e[0] == '0');
+}
+
+template <class Src, class Epi, int AUX>
+static int launch_pass_async(const fft::Plan& pl, int p, bool inverse, int batch, int ipc, Src src, Epi epi,
+                             cudaStream_t s) {
+  if (batch <= 0) return SGX_OK;
+  const fft::Pass& P = pl.pass[p];
+  const int groups = (batch + ipc - 1) / ipc;
+  if (groups > 65535) return fail(SGX_ERR_ARG, "launch_pass_async", "batch exceeds gridDim.y");
+  dim3 grid(P.ntiles, groups, 1);
+#define SGX_FFT_GO(INV, BIG)                                                                              \
+  {                                                                                                       \
+    auto kfn = fft::fft_pass_async_kernel<Src, Epi, INV, BIG, AUX>;                                       \
+    SGX_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_async[p])); \
+    SGX_COUNTED_LAUNCH(kfn, grid, dim3(fft::FFT_THREADS), pl.smem_async[p], s, P, src, epi, batch, ipc);  \
+  }
+  if (inverse) { if (pl.big) SGX_FFT_GO(true, true) else SGX_FFT_GO(true, false) }
+  else         { if (pl.big) SGX_FFT_GO(false, true) else SGX_FFT_GO(false, false) }
+#undef SGX_FFT_GO
+  SGX_CUDA(cudaGetLastError());
+  return SGX_OK;
+}
+
+// items per CTA of the persistent pass kernel: enough CTAs to fill the GPU a few times over
+static int pick_ipc(int batch, int ntiles) {
+  const int target_ctas = 148 * 2 * 3;
+  int ipc = (int)(((long long)batch * ntiles + target_ctas - 1) / target_ctas);
+  if (ipc < 1) ipc = 1;
+  if (ipc > 32) ipc = 32;
+  return ipc;
+}
+
+// Complex-input transform with the first operand formed as src x aux (AUX_SAME) in pass 0; later
+// passes use the twiddle table as the second operand.  Falls back to the synchronous kernels when a
+// pass cannot take the async path.
+template <class Src0, class Epi>
+static int run_fft_async(const fft::Plan& pl, bool inverse, int batch, Src0 src0, Epi epi, cpx* w0, cpx* w1,
+                         cudaStream_t s) {
+  const long long n = pl.N;
+  for (int p = 0; p < pl.npass; ++p)
+    if (!pl.async_ok[p]) return fail(SGX_ERR_ARG, "run_fft_async", "pass layout not supported");
+  cpx* cur = w0;
+  cpx* oth = w1;
+  int rc;
+  if (pl.npass == 1) return launch_pass_async<Src0, Epi, fft::AUX_SAME>(pl, 0, inverse, batch, pick_ipc(batch, pl.pass[0].ntiles), src0, epi, s);
+  rc = launch_pass_async<Src0, fft::StoreCpx, fft::AUX_SAME>(pl, 0, inverse, batch, pick_ipc(batch, pl.pass[0].ntiles), src0,
+                                                             fft::StoreCpx{cur, n, 1.f, 0, nullptr}, s);
+  if (rc) return rc;
+  for (int p = 1; p + 1 < pl.npass; ++p) {
+    rc = launch_pass_async<fft::SrcPlain, fft::StoreCpx, fft::AUX_TWIDDLE>(
+        pl, p, inverse, batch, pick_ipc(batch, pl.pass[p].ntiles), fft::SrcPlain{cur, n, pl.pass[p].twg},
+        fft::StoreCpx{oth, n, 1.f, 0, nullptr}, s);
+    if (rc) return rc;
+    cpx* t = cur; cur = oth; oth = t;
+  }
+  const int last = pl.npass - 1;
+  return launch_pass_async<fft::SrcPlain, Epi, fft::AUX_TWIDDLE>(pl, last, inverse, batch, pick_ipc(batch, pl.pass[last].ntiles),
+                                                                 fft::SrcPlain{cur, n, pl.pass[last].twg}, epi, s);
+}
+
+// passes 1.. of a transform whose first pass was done by the synchronous kernel (int8 prologues)
+template <class Epi>
+static int run_fft_tail_async(const fft::Plan& pl, bool inverse, int batch, cpx* cur, cpx* oth, Epi epi, cudaStream_t s) {
+  const long long n = pl.N;
+  int rc;
+  for (int p = 1; p + 1 < pl.npass; ++p) {
+    rc = launch_pass_async<fft::SrcPlain, fft::StoreCpx, fft::AUX_TWIDDLE>(
+        pl, p, inverse, batch, pick_ipc(batch, pl.pass[p].ntiles), fft::SrcPlain{cur, n, pl.pass[p].twg},
+        fft::StoreCpx{oth, n, 1.f, 0, nullptr}, s);
+    if (rc) return rc;
+    cpx* t = cur; cur = oth; oth = t;
+  }
+  const int last = pl.npass - 1;
+  return launch_pass_async<fft::SrcPlain, Epi, fft::AUX_TWIDDLE>(pl, last, inverse, batch, pick_ipc(batch, pl.pass[last].ntiles),
+                                                                 fft::SrcPlain{cur, n, pl.pass[last].twg}, epi, s);
 }
 
 struct AcqPlan {
@@ -355,7 +466,7 @@ static int ensure_plan(const sgx_settings* st, const int8_t* ca_table, const int
   free(cps);
   // A5: conj(FFT(code)) / n for all 32 PRNs
   rc = run_fft(a.fwd, false, 32, ProCode{a.table.as<int8_t>(), n1},
-               fft::StoreCpx{a.codeF.as<cpx>(), (long long)a.n, 1.0f / (float)a.n, 1}, a.work0.as<cpx>(),
+               fft::StoreCpx{a.codeF.as<cpx>(), (long long)a.n, 1.0f / (float)a.n, 1, nullptr}, a.work0.as<cpx>(),
                a.work1.as<cpx>(), s);
   if (rc) return rc;
   a.valid = true;
@@ -403,7 +514,7 @@ extern "C" int sgx_acquire(const int8_t* sig, int64_t rec_stride, int64_t n_samp
   const int npr = R * prn_count;
   const int nt_last = a.inv.pass[a.inv.npass - 1].ntiles;
   // scratch
-  long long chunk_mb = 64;
+  long long chunk_mb = 256;
   if (const char* e = getenv("SGX_ACQ_CHUNK_MB")) chunk_mb = atoll(e) > 0 ? atoll(e) : chunk_mb;
   long long chunk = (chunk_mb << 20) / ((long long)sizeof(cpx) * n);
   if (chunk < 1) chunk = 1;
@@ -412,6 +523,9 @@ extern "C" int sgx_acquire(const int8_t* sig, int64_t rec_stride, int64_t n_samp
   if (wneed < npr) wneed = npr;
   if (wneed < 32) wneed = 32;
   const bool two_bufs = a.inv.npass > 2 || a.fwd.npass > 2;
+  bool async = use_async();
+  for (int p = 0; p < a.inv.npass; ++p) async = async && a.inv.async_ok[p];
+  for (int p = 0; p < a.fine.npass; ++p) async = async && a.fine.async_ok[p];
   if (a.spec.reserve(sizeof(cpx) * (size_t)nspec * n) || a.work0.reserve(sizeof(cpx) * (size_t)wneed * n) ||
       (two_bufs && a.work1.reserve(sizeof(cpx) * (size_t)wneed * n)) ||
       a.partial.reserve(sizeof(unsigned long long) * (size_t)nitems * nt_last) ||
@@ -428,15 +542,19 @@ extern "C" int sgx_acquire(const int8_t* sig, int64_t rec_stride, int64_t n_samp
   if (nspec > 32768 || npr > 32768)
     return fail(SGX_ERR_ARG, "sgx_acquire", "too many recordings in one call (split the batch)");
   rc = run_fft(a.fwd, false, nspec, ProNco{d_sig, stride, a.cps.as<double>(), nbins, blocks, (int)n, 0.0},
-               fft::StoreCpx{a.spec.as<cpx>(), n, 1.f, 0}, a.work0.as<cpx>(), a.work1.as<cpx>(), s);
+               fft::StoreCpx{a.spec.as<cpx>(), n, 1.f, 0, nullptr}, a.work0.as<cpx>(), a.work1.as<cpx>(), s);
   if (rc) return rc;
   // ---- A7: spectrum x code -> IFFT -> |.|^2 -> per-row arg-max, in L2-sized chunks -------------
   for (long long i0 = 0; i0 < nitems; i0 += chunk) {
     const int cnt = (int)((nitems - i0) < chunk ? (nitems - i0) : chunk);
     EpiPeak ep;
     ep.partial = a.partial.as<unsigned long long>(); ep.ntiles = nt_last; ep.item0 = i0; ep.best = 0; ep.n1 = n1;
-    rc = run_fft(a.inv, true, cnt, ProMul{a.spec.as<cpx>(), a.codeF.as<cpx>(), d, (int)n, i0}, ep, a.work0.as<cpx>(),
-                 a.work1.as<cpx>(), s);
+    if (async)
+      rc = run_fft_async(a.inv, true, cnt, SrcMul{a.spec.as<cpx>(), a.codeF.as<cpx>(), d, (int)n, i0}, ep,
+                         a.work0.as<cpx>(), a.work1.as<cpx>(), s);
+    else
+      rc = run_fft(a.inv, true, cnt, ProMul{a.spec.as<cpx>(), a.codeF.as<cpx>(), d, (int)n, i0}, ep, a.work0.as<cpx>(),
+                   a.work1.as<cpx>(), s);
     if (rc) return rc;
   }
   // ---- A8 + A9 -------------------------------------------------------------------------------
@@ -446,8 +564,12 @@ extern "C" int sgx_acquire(const int8_t* sig, int64_t rec_stride, int64_t n_samp
     EpiSecond es;
     es.partial = a.partial2.as<unsigned long long>(); es.sel = a.sel.as<PeakSel>(); es.ntiles = nt_last;
     es.chip = st->samplesPerCodeChip; es.n = n1; es.best = 0; es.cp = 0;   // candidates within one code period
-    rc = run_fft(a.inv, true, npr, ProMulSel{a.spec.as<cpx>(), a.codeF.as<cpx>(), a.sel.as<PeakSel>(), d, (int)n}, es,
-                 a.work0.as<cpx>(), a.work1.as<cpx>(), s);
+    if (async)
+      rc = run_fft_async(a.inv, true, npr, SrcMulSel{a.spec.as<cpx>(), a.codeF.as<cpx>(), a.sel.as<PeakSel>(), d, (int)n},
+                         es, a.work0.as<cpx>(), a.work1.as<cpx>(), s);
+    else
+      rc = run_fft(a.inv, true, npr, ProMulSel{a.spec.as<cpx>(), a.codeF.as<cpx>(), a.sel.as<PeakSel>(), d, (int)n}, es,
+                   a.work0.as<cpx>(), a.work1.as<cpx>(), s);
     if (rc) return rc;
   }
   SGX_COUNTED_LAUNCH(metric_kernel, dim3((npr + 127) / 128), dim3(128), 0, s, a.partial2.as<unsigned long long>(),
@@ -500,7 +622,13 @@ extern "C" int sgx_acquire(const int8_t* sig, int64_t rec_stride, int64_t n_samp
       ef.hi = uniq - 5; ef.best = 0;
       ProFine pf{d_sig, stride, (const long long*)a.sums.p, (long long)n_samples, a.chips.as<int8_t>(),
                  a.fidx.as<unsigned short>(), a.fitems.as<FineItem>() + f0, a.nvalid, 0.f};
-      rc = run_fft(a.fine, false, cnt, pf, ef, a.work0.as<cpx>(), a.work1.as<cpx>(), s);
+      if (async && a.fine.npass >= 2) {
+        // pass 0 (int8 prologue) stays synchronous; the remaining passes stream through the async kernel
+        rc = launch_pass(a.fine, 0, false, cnt, pf, fft::StoreCpx{a.work0.as<cpx>(), (long long)a.nfft, 1.f, 0, nullptr}, s);
+        if (!rc) rc = run_fft_tail_async(a.fine, false, cnt, a.work0.as<cpx>(), a.work1.as<cpx>(), ef, s);
+      } else {
+        rc = run_fft(a.fine, false, cnt, pf, ef, a.work0.as<cpx>(), a.work1.as<cpx>(), s);
+      }
       if (rc) return rc;
     }
     SGX_COUNTED_LAUNCH(fine_reduce_kernel, dim3((nf + 127) / 128), dim3(128), 0, s, a.fpartial.as<unsigned long long>(),
@@ -538,8 +666,8 @@ extern "C" int sgx_fft_c2c(const float* in, float* out, int32_t n, int32_t batch
   if (bin.reserve(bytes) || bout.reserve(bytes) || w0.reserve(bytes) || w1.reserve(bytes))
     return fail(SGX_ERR_CUDA, "cudaMalloc", "fft test buffers");
   SGX_CUDA(cudaMemcpyAsync(bin.p, in, bytes, cudaMemcpyHostToDevice, s));
-  rc = run_fft(pl, inverse != 0, batch, fft::LoadCpx{bin.as<cpx>(), (long long)n},
-               fft::StoreCpx{bout.as<cpx>(), (long long)n, 1.f, 0}, w0.as<cpx>(), w1.as<cpx>(), s);
+  rc = run_fft(pl, inverse != 0, batch, fft::LoadCpx{bin.as<cpx>(), (long long)n, nullptr},
+               fft::StoreCpx{bout.as<cpx>(), (long long)n, 1.f, 0, nullptr}, w0.as<cpx>(), w1.as<cpx>(), s);
   if (rc) return rc;
   SGX_CUDA(cudaMemcpyAsync(out, bout.p, bytes, cudaMemcpyDeviceToHost, s));
   SGX_CUDA(cudaStreamSynchronize(s));

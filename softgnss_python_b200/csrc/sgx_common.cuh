@@ -71,6 +71,14 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc) : "memory");
 #endif
 }
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+#ifdef SGX_EMUL
+  memcpy(smem_dst, gsrc, 8);
+#else
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gsrc) : "memory");
+#endif
+}
 __device__ __forceinline__ void cp_async_commit() {
 #ifndef SGX_EMUL
   asm volatile("cp.async.commit_group;\n" ::: "memory");

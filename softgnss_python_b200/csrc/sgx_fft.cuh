@@ -234,23 +234,169 @@ __global__ void __launch_bounds__(FFT_THREADS) fft_pass_kernel(Pass P, Pro pro, 
   epi.finish(batch, tile);
 }
 
+// ---- asynchronous, persistent variant of the pass kernel ----------------------------------------
+// Same mathematics as fft_pass_kernel, restructured after the first ncu captures (profiles/): the
+// synchronous version spent ~65 % of its warp samples waiting for the global loads of the tile.  Here
+//  * a CTA owns one tile position (16 columns) and walks over `items_per_cta` consecutive transforms;
+//  * the streamed operand of a transform is staged with cp.async (no register staging, all rows in
+//    flight at once) into shared memory;
+//  * the second operand -- the inter-pass twiddle tile, or the code-spectrum tile of the current PRN
+//    -- stays in shared memory and is reloaded only when it changes, which also removes the L2 hot
+//    spot of dozens of CTAs re-reading the same lines;
+//  * the product of the two is formed while the first butterfly reads its inputs.
+enum AuxKind { AUX_NONE = 0, AUX_SAME = 1, AUX_TWIDDLE = 2 };
+
+// Src:  int locate(int batch, const cpx*& src, const cpx*& aux) const   -> AuxKind
+template <int r, bool INV, int AUX>
+__device__ __forceinline__ void subpass_first(const cpx* __restrict__ s1, const cpx* __restrict__ s2,
+                                              cpx* __restrict__ out, int R) {
+  const int mm = R / r;
+  const int total = mm * TILE;
+  for (int idx = threadIdx.x; idx < total; idx += FFT_THREADS) {
+    const int jj = idx & (TILE - 1);
+    const int b = idx / TILE;
+    cpx v[r];
+#pragma unroll
+    for (int u = 0; u < r; ++u) {
+      const int e = (b + u * mm) * TILE + jj;
+      cpx x = s1[e];
+      if (AUX != AUX_NONE) {
+        cpx w = s2[e];
+        if (AUX == AUX_TWIDDLE && INV) w.y = -w.y;
+        x = cmulf(x, w);
+      }
+      v[u] = x;
+    }
+    Dft<r, INV>::run(v);
+    const int base = b * r;   // ls == 1
+#pragma unroll
+    for (int u = 0; u < r; ++u) out[(base + u) * TILE_P + jj] = v[u];
+  }
+}
+
+template <bool INV, bool BIG, int AUX>
+__device__ __forceinline__ void run_subpass_first(int r, const cpx* s1, const cpx* s2, cpx* out, int R) {
+  switch (r) {
+    case 2: subpass_first<2, INV, AUX>(s1, s2, out, R); break;
+    case 4: subpass_first<4, INV, AUX>(s1, s2, out, R); break;
+    case 8: subpass_first<8, INV, AUX>(s1, s2, out, R); break;
+    case 16: subpass_first<16, INV, AUX>(s1, s2, out, R); break;
+    default:
+      if (BIG) {
+        switch (r) {
+          case 3: subpass_first<3, INV, AUX>(s1, s2, out, R); break;
+          case 5: subpass_first<5, INV, AUX>(s1, s2, out, R); break;
+          case 7: subpass_first<7, INV, AUX>(s1, s2, out, R); break;
+          case 11: subpass_first<11, INV, AUX>(s1, s2, out, R); break;
+          case 31: subpass_first<31, INV, AUX>(s1, s2, out, R); break;
+        }
+      }
+  }
+}
+
+template <class Src, class Epi, bool INV, bool BIG, int AUX>
+__global__ void __launch_bounds__(FFT_THREADS) fft_pass_async_kernel(Pass P, Src srcd, Epi epi, int n_batch,
+                                                                      int items_per_cta) {
+  SGX_DYN_SMEM(smem);
+  const int R = P.R, m = P.m, Ls = P.Ls;
+  cpx* S1 = reinterpret_cast<cpx*>(smem);          // staged operand [R][16]; later a padded work buffer
+  cpx* A = S1 + R * TILE_P;                        // padded work buffer [R][17]
+  cpx* S2 = A + R * TILE_P;                        // second operand tile [R][16]
+  cpx* W = S2 + R * TILE;
+  const int tid = threadIdx.x;
+  const int tile = blockIdx.x;
+  const int j0 = tile * TILE;
+  const int ncol = min(TILE, m - j0);
+  const int jj = tid & (TILE - 1), t0 = tid / TILE;
+  const int j = j0 + jj;
+  const bool valid = j < m;
+  const int k = Ls > 1 ? j % Ls : 0;
+  const int k0 = Ls > 1 ? j0 % Ls : 0;
+  const int b_begin = blockIdx.y * items_per_cta;
+  const int b_end = min(n_batch, b_begin + items_per_cta);
+
+  for (int q = tid; q < R; q += FFT_THREADS) {
+    cpx w = P.wr[q];
+    if (INV) w.y = -w.y;
+    W[q] = w;
+  }
+  const cpx* aux_cached = nullptr;
+  for (int batch = b_begin; batch < b_end; ++batch) {
+    const cpx* src;
+    const cpx* aux;
+    srcd.locate(batch, src, aux);
+    if (AUX != AUX_NONE && aux != aux_cached) {
+      if (AUX == AUX_SAME) {
+        for (int t = t0; t < R; t += ROWS_PER_ITER)
+          if (valid) cp_async8(&S2[t * TILE + jj], aux + (size_t)t * m + j);
+      } else {
+        for (int t = t0; t < R; t += ROWS_PER_ITER)
+          if (valid) cp_async8(&S2[t * TILE + jj], aux + (size_t)t * Ls + k0 + jj);
+      }
+      aux_cached = aux;
+    }
+    for (int t = t0; t < R; t += ROWS_PER_ITER)
+      if (valid) cp_async8(&S1[t * TILE + jj], src + (size_t)t * m + j);
+    cp_async_commit();
+    cp_async_wait_all();
+    __syncthreads();
+    // first sub-pass: staged operands -> A
+    run_subpass_first<INV, BIG, AUX>(P.radix[0], S1, S2, A, R);
+    __syncthreads();
+    cpx* cur = A;
+    cpx* oth = S1;
+    int ls = P.radix[0];
+    for (int s = 1; s < P.nsub; ++s) {
+      const int r = P.radix[s];
+      run_subpass<INV, BIG>(r, cur, oth, W, R, ls);
+      ls *= r;
+      __syncthreads();
+      cpx* tmp = cur; cur = oth; oth = tmp;
+    }
+    epi.begin(batch);
+    if (Ls == 1) {
+      for (int c = 0; c < ncol; ++c) {
+        const int base = (j0 + c) * R;
+        for (int u = tid; u < R; u += FFT_THREADS) epi.put(base + u, cur[u * TILE_P + c]);
+      }
+    } else if (valid) {
+      const int base = (j - k) * R + k;
+#pragma unroll 4
+      for (int u = t0; u < R; u += ROWS_PER_ITER) epi.put(base + u * Ls, cur[u * TILE_P + jj]);
+    }
+    epi.finish(batch, tile);
+    __syncthreads();   // S1 / A are overwritten by the next transform
+  }
+}
+
 // ---- generic prologues / epilogues -----------------------------------------------------------
 struct LoadCpx {  // plain complex input, transforms `stride` apart
   const cpx* in;
   long long stride;
-  __device__ __forceinline__ void prepare(int batch) { in += (long long)batch * stride; }
-  __device__ __forceinline__ cpx load(int n) const { return in[n]; }
+  const cpx* cur;
+  __device__ __forceinline__ void prepare(int batch) { cur = in + (long long)batch * stride; }
+  __device__ __forceinline__ cpx load(int n) const { return cur[n]; }
 };
 struct StoreCpx {
   cpx* out;
   long long stride;
   float scale;   // applied to both parts
   int conj;      // store the conjugate
-  __device__ __forceinline__ void begin(int batch) { out += (long long)batch * stride; }
+  cpx* cur;
+  __device__ __forceinline__ void begin(int batch) { cur = out + (long long)batch * stride; }
   __device__ __forceinline__ void put(int n, cpx v) const {
-    out[n] = make_float2(v.x * scale, conj ? -v.y * scale : v.y * scale);
+    cur[n] = make_float2(v.x * scale, conj ? -v.y * scale : v.y * scale);
   }
   __device__ __forceinline__ void finish(int, int) {}
+};
+struct SrcPlain {  // async variant: plain complex input (+ the pass' twiddle table as second operand)
+  const cpx* in;
+  long long stride;
+  const cpx* tw;
+  __device__ __forceinline__ void locate(int batch, const cpx*& src, const cpx*& aux) const {
+    src = in + (long long)batch * stride;
+    aux = tw;
+  }
 };
 
 // packed (value, index) key: larger value wins, then the smaller index (numpy arg-max tie rule)
@@ -298,6 +444,8 @@ struct Plan {
   Pass pass[4];
   DevBuf tw[4], wr[4];
   size_t smem[4];
+  size_t smem_async[4];
+  bool async_ok[4];
 };
 
 inline bool factor_small(int n, int* radices, int& cnt) {
@@ -384,6 +532,8 @@ inline int build_plan(Plan& pl, int N, bool inverse, cudaStream_t s, int maxR = 
     P.ntiles = (P.m + TILE - 1) / TILE;
     P.inverse = inverse ? 1 : 0;
     pl.smem[p] = sizeof(cpx) * ((size_t)2 * P.R * TILE_P + P.R);
+    pl.smem_async[p] = sizeof(cpx) * ((size_t)2 * P.R * TILE_P + (size_t)P.R * TILE + P.R);
+    pl.async_ok[p] = (Ls == 1) || (Ls % TILE == 0) || (P.m <= Ls);   // twiddle rows of a tile must not wrap
     if (pl.wr[p].reserve(sizeof(cpx) * P.R)) return fail(SGX_ERR_CUDA, "cudaMalloc", "fft tables");
     SGX_COUNTED_LAUNCH(twiddle_kernel, dim3(4), dim3(128), 0, s, pl.wr[p].as<cpx>(), (long long)P.R, 0, (long long)P.R);
     P.wr = pl.wr[p].as<cpx>();
