@@ -280,14 +280,16 @@ __global__ void metric_kernel(const unsigned long long* partial2, int ntiles, co
 }
 
 __global__ void fine_reduce_kernel(const unsigned long long* partial, int ntiles, int nitems, int* index) {
-  const int item = blockIdx.x * blockDim.x + threadIdx.x;
+  // one block per detected PRN: arg-max over the per-tile keys of the last fine-search pass
+  const int item = blockIdx.x;
   if (item >= nitems) return;
   unsigned long long best = 0ull;
-  for (int t = 0; t < ntiles; ++t) {
+  for (int t = threadIdx.x; t < ntiles; t += blockDim.x) {
     const unsigned long long k = partial[(long long)item * ntiles + t];
     best = k > best ? k : best;
   }
-  index[item] = (int)fft::key_index(best);
+  best = fft::block_max_key(best);
+  if (threadIdx.x == 0) index[item] = (int)fft::key_index(best);
 }
 
 // ------------------------------------------------------------------------------ host side
@@ -631,7 +633,7 @@ extern "C" int sgx_acquire(const int8_t* sig, int64_t rec_stride, int64_t n_samp
       }
       if (rc) return rc;
     }
-    SGX_COUNTED_LAUNCH(fine_reduce_kernel, dim3((nf + 127) / 128), dim3(128), 0, s, a.fpartial.as<unsigned long long>(),
+    SGX_COUNTED_LAUNCH(fine_reduce_kernel, dim3(nf), dim3(fft::FFT_THREADS), 0, s, a.fpartial.as<unsigned long long>(),
                        nt_f, nf, a.findex.as<int>());
     SGX_CUDA(cudaGetLastError());
     int* h_idx = (int*)malloc(sizeof(int) * nf);

@@ -85,13 +85,25 @@ class RecordingSpec(object):
             fcode = Fraction(1023000) * (1 + Fraction(s.doppler) / Fraction(L1_HZ))
             dcp = int(round(fcode / Fraction(self.fs) * (1 << 32)))
             self.dcp[i] = dcp
-            # a code period starts exactly at sample code_phase: cp0 + code_phase*dcp == 0 (mod 1023 chips);
-            # one full period is added so that cp never has to go negative.
-            self.cp0[i] = (code_mod - (s.code_phase * dcp) % code_mod) % code_mod
-            # the period running at n=0 is period 0; the one starting at code_phase is period 1
-            # (or 0 when code_phase == 0).  bit index = (period + per0) // 20.
-            first = 0 if s.code_phase == 0 or self.cp0[i] == 0 else 1
-            self.per0[i] = (s.bit_offset_ms - first) % 20
+            sync = getattr(s, "frame_sync", None)
+            if sync is not None:
+                # (sample index n_s at which nav bit number b0 of the stream starts, b0): the code period
+                # that starts at n_s is the first of that bit
+                n_s, b0 = int(sync[0]), int(sync[1])
+                self.cp0[i] = (code_mod - (n_s * dcp) % code_mod) % code_mod
+                periods_at_ns = (int(self.cp0[i]) + n_s * dcp) // code_mod
+                self.per0[i] = 20 * b0 - periods_at_ns
+                assert self.per0[i] >= 0, "nav stream must start before sample 0"
+                cp0 = int(self.cp0[i])
+                s.code_phase = 0 if cp0 == 0 else -(-(code_mod - cp0) // dcp)   # first period start >= 0
+            else:
+                # a code period starts exactly at sample code_phase: cp0 + code_phase*dcp == 0 (mod 1023
+                # chips); one full period is added so that cp never has to go negative.
+                self.cp0[i] = (code_mod - (s.code_phase * dcp) % code_mod) % code_mod
+                # the period running at n=0 is period 0; the one starting at code_phase is period 1
+                # (or 0 when code_phase == 0).  bit index = (period + per0) // 20.
+                first = 0 if s.code_phase == 0 or self.cp0[i] == 0 else 1
+                self.per0[i] = (s.bit_offset_ms - first) % 20
             if s.nav_bits is not None:
                 nb = min(len(s.nav_bits), self.n_bits)
                 self.bits[i, :nb] = s.nav_bits[:nb]
