@@ -31,18 +31,33 @@ def needs_build():
 
 
 def build_native(force=False, verbose=False):
+    """nvcc -> in-tree libsoftgnss_b200.so; the translation units are compiled in parallel."""
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
-    cmd = [nvcc] + flags + ["-shared", "-o", LIB] + _sources()
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    procs = []
+    for src in _sources():
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        procs.append((src, obj, subprocess.Popen([nvcc] + flags + ["-c", "-o", obj, src], stdout=subprocess.PIPE,
+                                                 stderr=subprocess.PIPE, text=True)))
+    report, objs = [], []
+    for src, obj, p in procs:
+        out, err = p.communicate()
+        report.append(err)
+        if verbose or p.returncode != 0:
+            sys.stderr.write(out + err)
+        if p.returncode != 0:
+            raise RuntimeError("nvcc failed on " + src)
+        objs.append(obj)
+    res = subprocess.run([nvcc, "-shared", "-o", LIB] + objs, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed: " + " ".join(cmd))
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("link failed")
     with open(os.path.join(HERE, "csrc", "ptxas_report.txt"), "w") as f:
-        f.write(res.stderr)
+        f.write("".join(report))
     return LIB
 
 

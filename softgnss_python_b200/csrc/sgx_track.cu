@@ -316,7 +316,7 @@ __device__ __forceinline__ void correlate_segments(const MsParams& P, const int8
         if (bl != b) irregular = true;
       }
     }
-    beta[s] = min(b, P.blk);
+    beta[s] = max(0, min(b, P.blk));   // (a prediction of -1 occurs when rem is within rounding of one step)
   }
   if (beta[0] >= P.blk) return;
   if (irregular) {
@@ -446,7 +446,171 @@ __device__ __forceinline__ void correlate_segments(const MsParams& P, const int8
   tEr += (double)fEr; tEi += (double)fEi; tPr += (double)fPr; tPi += (double)fPi; tLr += (double)fLr; tLi += (double)fLi;
 }
 
-template <bool BULK, int NW>
+// ---- correlate, variant C: half-chip segments with exact integer segment sums --------------------
+// Same segmentation as variant B.  The per-sample twiddles w^k are quantised once per period to Q30
+// fixed point and split into four signed base-256 digits, so a segment sum is 8 dot products per four
+// samples (dp4a, int32 accumulation is exact); rotors, code signs and all accumulation are float64.
+// The only approximation left is the 2^-31 twiddle quantisation (relative error of a correlator
+// output ~5e-11), which keeps the carried code phase within ~1e-11 chips of the reference's and makes
+// chip reassignments a once-per-many-minutes event instead of a per-second one.
+struct ExactTables {
+  signed char tw[2][4][32];   // [re/im][digit][k], read as packed words
+  double z[5][2];             // rotor steps e^{j 2 pi (LMAX-4+j) cps}
+};
+
+__device__ __forceinline__ void cis_cycles_f64(double cyc, double& c, double& s) {
+  cyc -= rint(cyc);
+  sincospi(2.0 * cyc, &s, &c);
+}
+
+// executed by the 32 lanes of the carrier thread's warp once the next period's cps is known
+template <int NW>
+__device__ __forceinline__ void build_exact_tables(ExactTables& T, double cps, int lane) {
+  constexpr int LMAX = 4 * NW;
+  if (lane < LMAX) {
+    double c, s;
+    cis_cycles_f64((double)lane * cps, c, s);
+    long long w[2] = {__double2ll_rn(c * 1073741824.0), __double2ll_rn(s * 1073741824.0)};
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      long long v = w[q];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const long long b = ((v + 128) & 0xFF) - 128;   // signed digit in [-128, 127]
+        T.tw[q][d][lane] = (signed char)b;
+        v = (v - b) >> 8;
+      }
+      T.tw[q][3][lane] = (signed char)v;                // |v| <= 65
+    }
+  }
+  // rotor steps: on spare lanes next to the twiddle lanes when there are any, else afterwards
+  constexpr int Z0 = (LMAX + 5 <= 32) ? LMAX : 0;
+  if (lane >= Z0 && lane < Z0 + 5) {
+    const int j = lane - Z0;
+    cis_cycles_f64((double)(LMAX - 4 + j) * cps, T.z[j][0], T.z[j][1]);
+  }
+}
+
+template <int NW>
+__device__ __forceinline__ void correlate_exact(const MsParams& P, const int8_t* cur, const double* codeD,
+                                                const ExactTables& T, int tid, double& tEr, double& tEi,
+                                                double& tPr, double& tPi, double& tLr, double& tLi) {
+  constexpr int SEGS = 8;
+  constexpr int LMAX = 4 * NW;
+  const int off = (int)(P.pos - (P.pos & ~15LL));
+  const int n0 = SEGS * tid - 1;
+  int beta[SEGS + 1];
+  bool irregular = false;
+  const double h = 0.5 * P.inv_step, q0 = -P.startP * P.inv_step;
+#pragma unroll
+  for (int s = 0; s <= SEGS; ++s) {
+    const int n = n0 + s;
+    int b;
+    if (n < 0) b = 0;
+    else if (n > 2046) b = P.blk;
+    else {
+      // boundaries are equally spaced in the predicted (real-valued) sample index: q_n = (n/2 - rem) / step
+      const double q = fma((double)n, h, q0);
+      const double fl = floor(q);
+      b = (int)fl + 1;
+      const double fr = q - fl;
+      if (fr < 1e-6 || fr > 1.0 - 1e-6) {   // too close to a sample instant: settle with the exact expressions
+        if ((n & 1) == 0) b = next_event(n >> 1, P.startP, P.stepP, P.inv_step);
+        else {
+          const int c = (n - 1) >> 1;
+          b = next_event(c, P.startE, P.stepE, P.inv_step);
+          const int bl = next_event(c + 1, P.startL, P.stepL, P.inv_step);
+          if (bl != b) irregular = true;
+        }
+      }
+    }
+    beta[s] = max(0, min(b, P.blk));   // (a prediction of -1 occurs when rem is within rounding of one step)
+  }
+  if (beta[0] >= P.blk) return;
+  bool too_long = false;
+#pragma unroll
+  for (int s = 0; s < SEGS; ++s) too_long = too_long || (beta[s + 1] - beta[s] > LMAX);
+  if (irregular || too_long) {
+    // exact per-sample evaluation (tracking.py:166-219 verbatim, float64)
+    for (int i = beta[0]; i < beta[SEGS]; ++i) {
+      const int ie = (int)ceil(lin_y(i, P.stepE, P.startE));
+      const int ip = (int)ceil(lin_y(i, P.stepP, P.startP));
+      const int il = (int)ceil(lin_y(i, P.stepL, P.startL));
+      double cs, sn;
+      cis_cycles_f64((double)i * P.cps + P.rem_cyc, cs, sn);
+      const double x = (double)cur[off + i];
+      const double pr = x * cs, pi = x * sn;
+      tEr += codeD[ie] * pr; tEi += codeD[ie] * pi;
+      tPr += codeD[ip] * pr; tPi += codeD[ip] * pi;
+      tLr += codeD[il] * pr; tLi += codeD[il] * pi;
+    }
+    return;
+  }
+  // packed twiddle digits: tw[c][d] word q holds samples 4q .. 4q+3
+  int twr[4][NW], twi[4][NW];
+#pragma unroll
+  for (int d = 0; d < 4; ++d)
+#pragma unroll
+    for (int q = 0; q < NW; ++q) {
+      twr[d][q] = reinterpret_cast<const int*>(T.tw[0][d])[q];
+      twi[d][q] = reinterpret_cast<const int*>(T.tw[1][d])[q];
+    }
+  double rotr = 1.0, roti = 0.0;
+  double aEr = 0, aEi = 0, aPr = 0, aPi = 0, aLr = 0, aLi = 0;
+  bool fresh = true;
+#pragma unroll
+  for (int s = 0; s < SEGS; ++s) {
+    const int a = beta[s];
+    const int b = beta[s + 1];
+    if (b <= a) continue;
+    const int n = n0 + s;
+    const double sP = codeD[(n >> 1) + 1];
+    const int ie = (n + 1) >> 1;
+    const double sE = codeD[ie], sL = codeD[ie + 1];
+    if (fresh) {
+      cis_cycles_f64((double)a * P.cps + P.rem_cyc, rotr, roti);
+      fresh = false;
+    }
+    const int len = b - a;
+    const int addr = off + a;
+    const unsigned* wp = reinterpret_cast<const unsigned*>(cur + (addr & ~3));
+    const int sh = (addr & 3) * 8;
+    unsigned raw[NW + 1];
+#pragma unroll
+    for (int q = 0; q <= NW; ++q) raw[q] = wp[q];
+    int xr[4] = {0, 0, 0, 0}, xi[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int q = 0; q < NW; ++q) {
+      unsigned w = __funnelshift_r(raw[q], raw[q + 1], sh);
+      const int keep = len - 4 * q;
+      if (keep < 4) w &= keep <= 0 ? 0u : (0xFFFFFFFFu >> (8 * (4 - keep)));
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        xr[d] = __dp4a((int)w, twr[d][q], xr[d]);
+        xi[d] = __dp4a((int)w, twi[d][q], xi[d]);
+      }
+    }
+    // exact recombination of the base-256 digits (|value| < 2^45, exact in float64)
+    const double Sr = fma(fma(fma((double)xr[3], 256.0, (double)xr[2]), 256.0, (double)xr[1]), 256.0, (double)xr[0]);
+    const double Si = fma(fma(fma((double)xi[3], 256.0, (double)xi[2]), 256.0, (double)xi[1]), 256.0, (double)xi[0]);
+    const double Rr = rotr * Sr - roti * Si, Ri = rotr * Si + roti * Sr;
+    aEr += sE * Rr; aEi += sE * Ri;
+    aPr += sP * Rr; aPi += sP * Ri;
+    aLr += sL * Rr; aLi += sL * Ri;
+    const int j = len - (LMAX - 4);
+    if (j >= 0) {
+      const double zr = T.z[j][0], zi = T.z[j][1];
+      const double nr = rotr * zr - roti * zi, ni = rotr * zi + roti * zr;
+      rotr = nr; roti = ni;
+    } else {
+      fresh = true;
+    }
+  }
+  const double sc = 9.313225746154785e-10;   // 2^-30
+  tEr += aEr * sc; tEi += aEi * sc; tPr += aPr * sc; tPi += aPi * sc; tLr += aLr * sc; tLi += aLi * sc;
+}
+
+template <bool BULK, int NW, bool EXACT>
 __global__ void __launch_bounds__(TRK_THREADS, 2) track_kernel(TrackArgs a) {
   SGX_DYN_SMEM(smem);
   int8_t* buf0 = (int8_t*)smem;
@@ -455,6 +619,8 @@ __global__ void __launch_bounds__(TRK_THREADS, 2) track_kernel(TrackArgs a) {
   __shared__ double red[TRK_WARPS][6];
   __shared__ float codeS[1040];  // 1025 used; the tail absorbs indices reached only by masked samples
   __shared__ unsigned long long mbar[2];
+  __shared__ ExactTables xt;
+  __shared__ double codeD[EXACT ? 1040 : 1];
 
   const int tid = threadIdx.x;
   const int cid = blockIdx.x;  // recording * n_channels + channel
@@ -469,7 +635,10 @@ __global__ void __launch_bounds__(TRK_THREADS, 2) track_kernel(TrackArgs a) {
   const long long rec_alloc = (rec_len + 15) & ~15LL;
   {  // padded code [c1022, c0..c1022, c0] (tracking.py:109-111)
     const int8_t* c = a.chips + (chn.prn - 1) * 1023;
-    for (int i = tid; i < 1040; i += TRK_THREADS) codeS[i] = i < 1025 ? (float)c[(i + 1022) % 1023] : 0.f;
+    for (int i = tid; i < 1040; i += TRK_THREADS) {
+      codeS[i] = i < 1025 ? (float)c[(i + 1022) % 1023] : 0.f;
+      if (EXACT) codeD[i] = (double)codeS[i];
+    }
   }
   CodeState cst;
   CarrState rst;
@@ -487,6 +656,10 @@ __global__ void __launch_bounds__(TRK_THREADS, 2) track_kernel(TrackArgs a) {
     rst.remCarrPhase = 0.0;
     rst.oldCarrNco = rst.oldCarrError = 0.0;
     prepare_carr(a, rst, prm);
+  }
+  if (EXACT && (tid >> 5) == 1) {   // the carrier thread's warp builds the twiddle / rotor tables
+    const double cps = __shfl_sync(0xffffffffu, tid == 32 ? prm.cps : 0.0, 0);
+    build_exact_tables<(NW > 0 ? NW : 1)>(xt, cps, tid & 31);
   }
   __syncthreads();
 
@@ -541,8 +714,9 @@ __global__ void __launch_bounds__(TRK_THREADS, 2) track_kernel(TrackArgs a) {
     }
 
     double tEr = 0.0, tEi = 0.0, tPr = 0.0, tPi = 0.0, tLr = 0.0, tLi = 0.0;
-    if (NW > 0) correlate_segments<(NW > 0 ? NW : 1)>(P, cur, codeS, tid, tEr, tEi, tPr, tPi, tLr, tLi);
-    else        correlate_groups(P, cur, codeS, tid, tEr, tEi, tPr, tPi, tLr, tLi);
+    if (EXACT)       correlate_exact<(NW > 0 ? NW : 1)>(P, cur, codeD, xt, tid, tEr, tEi, tPr, tPi, tLr, tLi);
+    else if (NW > 0) correlate_segments<(NW > 0 ? NW : 1)>(P, cur, codeS, tid, tEr, tEi, tPr, tPi, tLr, tLi);
+    else             correlate_groups(P, cur, codeS, tid, tEr, tEi, tPr, tPi, tLr, tLi);
     // I arm = sin (imaginary part), Q arm = cos (real part): tracking.py:205-207
     double v0 = warp_sum_f64(tEi), v1 = warp_sum_f64(tEr), v2 = warp_sum_f64(tPi), v3 = warp_sum_f64(tPr),
            v4 = warp_sum_f64(tLi), v5 = warp_sum_f64(tLr);
@@ -585,6 +759,10 @@ __global__ void __launch_bounds__(TRK_THREADS, 2) track_kernel(TrackArgs a) {
       o[2 * m] = rst.carrFreq;
       o[3 * m] = I_P; o[7 * m] = Q_P;
       o[11 * m] = carrError; o[12 * m] = carrNco;
+    }
+    if (EXACT && (tid >> 5) == 1 && k + 1 < a.ms) {
+      const double cps = __shfl_sync(0xffffffffu, tid == 32 ? prm.cps : 0.0, 0);
+      build_exact_tables<(NW > 0 ? NW : 1)>(xt, cps, tid & 31);
     }
     __syncthreads();
   }
@@ -685,24 +863,37 @@ extern "C" int sgx_track(const int8_t* rec, int64_t rec_stride, const int64_t* r
   // correlate variant: half-chip segments when a segment fits the unrolled path, else aligned groups
   const double half_chip = st->samplingFreq / (2.0 * st->codeFreqBasis);   // samples per half chip
   int nw = ((int)ceil(half_chip + 0.25) + 3) / 4;
-  if (const char* e = getenv("SGX_TRK_KERNEL")) { if (strcmp(e, "groups") == 0) nw = 0; }
+  bool exact = true;   // exact integer segment sums by default; "segments" = float32 variant, "groups" = any spacing
+  if (const char* e = getenv("SGX_TRK_KERNEL")) {
+    if (strcmp(e, "groups") == 0) nw = 0;
+    if (strcmp(e, "segments") == 0) exact = false;
+  }
   if (fabs(st->dllCorrelatorSpacing - 0.5) > 1e-12) nw = 0;                 // segment scheme assumes E/L at +-0.5 chip
   const bool bulk = use_bulk();
-#define SGX_TRK_GO(B, W)                                                                           \
+#define SGX_TRK_GO(B, W, X)                                                                        \
   {                                                                                                \
-    auto kfn = track_kernel<B, W>;                                                                 \
+    auto kfn = track_kernel<B, W, X>;                                                              \
     SGX_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
     SGX_COUNTED_LAUNCH(kfn, dim3(nch), dim3(TRK_THREADS), smem, s, a);                             \
   }
-#define SGX_TRK_PICK(W) { if (bulk) SGX_TRK_GO(true, W) else SGX_TRK_GO(false, W) }
-  switch (nw) {
-    case 2: SGX_TRK_PICK(2) break;
-    case 4: SGX_TRK_PICK(4) break;
-    case 5: SGX_TRK_PICK(5) break;
-    case 8: SGX_TRK_PICK(8) break;
-    default: SGX_TRK_PICK(0) break;
+#define SGX_TRK_EXACT(W) { if (bulk) SGX_TRK_GO(true, W, true) else SGX_TRK_GO(false, W, true) }
+  if (nw >= 1 && nw <= 8 && exact) {
+    switch (nw) {
+      case 1: SGX_TRK_EXACT(1) break;
+      case 2: SGX_TRK_EXACT(2) break;
+      case 3: SGX_TRK_EXACT(3) break;
+      case 4: SGX_TRK_EXACT(4) break;
+      case 5: SGX_TRK_EXACT(5) break;
+      case 6: SGX_TRK_EXACT(6) break;
+      case 7: SGX_TRK_EXACT(7) break;
+      default: SGX_TRK_EXACT(8) break;
+    }
+  } else if (nw == 5) {
+    if (bulk) SGX_TRK_GO(true, 5, false) else SGX_TRK_GO(false, 5, false)     // float32 segment variant (comparison)
+  } else {
+    if (bulk) SGX_TRK_GO(true, 0, false) else SGX_TRK_GO(false, 0, false)     // aligned groups: any rate / spacing
   }
-#undef SGX_TRK_PICK
+#undef SGX_TRK_EXACT
 #undef SGX_TRK_GO
   SGX_CUDA(cudaGetLastError());
   if (out_on_host) SGX_CUDA(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, s));

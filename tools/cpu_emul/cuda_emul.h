@@ -271,6 +271,7 @@ static inline double __fma_rn(double a, double b, double c) { return fma(a, b, c
 static inline int __double2int_ru(double x) { return (int)ceil(x); }
 static inline int __double2int_rd(double x) { return (int)floor(x); }
 static inline long long __double2ll_rd(double x) { return (long long)floor(x); }
+static inline long long __double2ll_rn(double x) { return (long long)llrint(x); }
 static inline double __int2double_rn(int x) { return (double)x; }
 static inline double __ll2double_rn(long long x) { return (double)x; }
 static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
@@ -290,6 +291,10 @@ static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned s) {
 }
 static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) {
   return (unsigned)(((((unsigned long long)hi) << 32) | lo) >> (sh & 31));
+}
+static inline int __dp4a(int a, int b, int c) {
+  for (int i = 0; i < 4; ++i) c += (int)(signed char)((a >> (8 * i)) & 0xFF) * (int)(signed char)((b >> (8 * i)) & 0xFF);
+  return c;
 }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
