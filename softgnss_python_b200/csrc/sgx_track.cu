@@ -56,6 +56,9 @@ struct MsParams {
   double inv_step;  // 1/codePhaseStep, used only to *predict* event indices
   double cps;       // carrier cycles per sample
   double rem_cyc;   // remCarrPhase in cycles
+  double w;         // carrFreq * 2.0 * pi (tracking.py:195), rad/s
+  double rem_rad;   // remCarrPhase, rad
+  double fs;
   long long pos;    // byte offset (within the recording) of sample 0 of this block
   int blk;
   int stop;         // 0 = run this period, else sgx_status / 1 = finished
@@ -160,6 +163,9 @@ __device__ void prepare_carr(const TrackArgs& a, CarrState& st, MsParams& p) {
   st.w = st.carrFreq * 2.0 * 3.141592653589793;                       // :195
   p.cps = (st.w / a.fs) * 0.15915494309189535;
   p.rem_cyc = st.remCarrPhase * 0.15915494309189535;
+  p.w = st.w;
+  p.rem_rad = st.remCarrPhase;
+  p.fs = a.fs;
 }
 
 // T6 carry (tracking.py:197): remCarrPhase after a block of `blk` samples
@@ -447,14 +453,15 @@ __device__ __forceinline__ void correlate_segments(const MsParams& P, const int8
 }
 
 // ---- correlate, variant C: half-chip segments with exact integer segment sums --------------------
-// Same segmentation as variant B.  The per-sample twiddles w^k are quantised once per period to Q30
-// fixed point and split into four signed base-256 digits, so a segment sum is 8 dot products per four
+// Same segmentation as variant B.  The per-sample twiddles w^k are quantised once per period to Q38
+// (Q30 for the widest segments) fixed point and split into five (four) signed base-256 digits, so a segment sum is 10 (8) dot products per four
 // samples (dp4a, int32 accumulation is exact); rotors, code signs and all accumulation are float64.
 // The only approximation left is the 2^-31 twiddle quantisation (relative error of a correlator
 // output ~5e-11), which keeps the carried code phase within ~1e-11 chips of the reference's and makes
 // chip reassignments a once-per-many-minutes event instead of a per-second one.
+template <int NW> struct ExactDigits { static constexpr int value = NW <= 5 ? 5 : 4; };   // Q38 twiddles when registers allow, else Q30
 struct ExactTables {
-  signed char tw[2][4][32];   // [re/im][digit][k], read as packed words
+  signed char tw[2][5][32];   // [re/im][digit][k], read as packed words
   double z[5][2];             // rotor steps e^{j 2 pi (LMAX-4+j) cps}
 };
 
@@ -467,20 +474,22 @@ __device__ __forceinline__ void cis_cycles_f64(double cyc, double& c, double& s)
 template <int NW>
 __device__ __forceinline__ void build_exact_tables(ExactTables& T, double cps, int lane) {
   constexpr int LMAX = 4 * NW;
+  constexpr int ND = ExactDigits<NW>::value;
   if (lane < LMAX) {
     double c, s;
     cis_cycles_f64((double)lane * cps, c, s);
-    long long w[2] = {__double2ll_rn(c * 1073741824.0), __double2ll_rn(s * 1073741824.0)};
+    const double one = (double)(1LL << (8 * ND - 2));      // Q30 (4 digits) or Q38 (5 digits)
+    long long w[2] = {__double2ll_rn(c * one), __double2ll_rn(s * one)};
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
       long long v = w[q];
 #pragma unroll
-      for (int d = 0; d < 3; ++d) {
+      for (int d = 0; d < ND - 1; ++d) {
         const long long b = ((v + 128) & 0xFF) - 128;   // signed digit in [-128, 127]
         T.tw[q][d][lane] = (signed char)b;
         v = (v - b) >> 8;
       }
-      T.tw[q][3][lane] = (signed char)v;                // |v| <= 65
+      T.tw[q][ND - 1][lane] = (signed char)v;           // |v| <= 65
     }
   }
   // rotor steps: on spare lanes next to the twiddle lanes when there are any, else afterwards
@@ -547,9 +556,10 @@ __device__ __forceinline__ void correlate_exact(const MsParams& P, const int8_t*
     return;
   }
   // packed twiddle digits: tw[c][d] word q holds samples 4q .. 4q+3
-  int twr[4][NW], twi[4][NW];
+  constexpr int ND = ExactDigits<NW>::value;
+  int twr[ND][NW], twi[ND][NW];
 #pragma unroll
-  for (int d = 0; d < 4; ++d)
+  for (int d = 0; d < ND; ++d)
 #pragma unroll
     for (int q = 0; q < NW; ++q) {
       twr[d][q] = reinterpret_cast<const int*>(T.tw[0][d])[q];
@@ -568,7 +578,9 @@ __device__ __forceinline__ void correlate_exact(const MsParams& P, const int8_t*
     const int ie = (n + 1) >> 1;
     const double sE = codeD[ie], sL = codeD[ie + 1];
     if (fresh) {
-      cis_cycles_f64((double)a * P.cps + P.rem_cyc, rotr, roti);
+      // the reference's own phase expression for sample a (tracking.py:193-195), evaluated in radians so
+      // that no rounded 1/(2 pi) scales a 6e4 rad argument (that error would be common to all threads)
+      sincos(P.w * ((double)a / P.fs) + P.rem_rad, &roti, &rotr);
       fresh = false;
     }
     const int len = b - a;
@@ -578,21 +590,24 @@ __device__ __forceinline__ void correlate_exact(const MsParams& P, const int8_t*
     unsigned raw[NW + 1];
 #pragma unroll
     for (int q = 0; q <= NW; ++q) raw[q] = wp[q];
-    int xr[4] = {0, 0, 0, 0}, xi[4] = {0, 0, 0, 0};
+    int xr[ND], xi[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) { xr[d] = 0; xi[d] = 0; }
 #pragma unroll
     for (int q = 0; q < NW; ++q) {
       unsigned w = __funnelshift_r(raw[q], raw[q + 1], sh);
       const int keep = len - 4 * q;
       if (keep < 4) w &= keep <= 0 ? 0u : (0xFFFFFFFFu >> (8 * (4 - keep)));
 #pragma unroll
-      for (int d = 0; d < 4; ++d) {
+      for (int d = 0; d < ND; ++d) {
         xr[d] = __dp4a((int)w, twr[d][q], xr[d]);
         xi[d] = __dp4a((int)w, twi[d][q], xi[d]);
       }
     }
-    // exact recombination of the base-256 digits (|value| < 2^45, exact in float64)
-    const double Sr = fma(fma(fma((double)xr[3], 256.0, (double)xr[2]), 256.0, (double)xr[1]), 256.0, (double)xr[0]);
-    const double Si = fma(fma(fma((double)xi[3], 256.0, (double)xi[2]), 256.0, (double)xi[1]), 256.0, (double)xi[0]);
+    // exact recombination of the base-256 digits (|value| < 2^52, exact in float64)
+    double Sr = (double)xr[ND - 1], Si = (double)xi[ND - 1];
+#pragma unroll
+    for (int d = ND - 2; d >= 0; --d) { Sr = fma(Sr, 256.0, (double)xr[d]); Si = fma(Si, 256.0, (double)xi[d]); }
     const double Rr = rotr * Sr - roti * Si, Ri = rotr * Si + roti * Sr;
     aEr += sE * Rr; aEi += sE * Ri;
     aPr += sP * Rr; aPi += sP * Ri;
@@ -606,7 +621,7 @@ __device__ __forceinline__ void correlate_exact(const MsParams& P, const int8_t*
       fresh = true;
     }
   }
-  const double sc = 9.313225746154785e-10;   // 2^-30
+  const double sc = 1.0 / (double)(1LL << (8 * ND - 2));   // 2^-30 or 2^-38
   tEr += aEr * sc; tEi += aEi * sc; tPr += aPr * sc; tPi += aPi * sc; tLr += aLr * sc; tLi += aLi * sc;
 }
 

@@ -47,7 +47,7 @@ def test_tracking_matches_reference_golden(native, recordings, name, stage, vari
     """Both staging paths (TMA bulk copy / cp.async) and the three correlator formulations (exact
     integer segment sums = default, float32 segments, float32 aligned 16-sample groups) against the
     reference's own output.  The exact variant must match without a single chip reassignment and to
-    1e-8 of full scale; the float32 variants to 1e-5 up to their first reassignment."""
+    1e-9 of full scale (observed 2e-11); the float32 variants to 1e-5 up to their first reassignment."""
     from softgnss_python_b200.tracking import tracking
     monkeypatch.setenv("SGX_TRK_STAGE", stage)
     monkeypatch.setenv("SGX_TRK_KERNEL", variant)
@@ -66,9 +66,9 @@ def test_tracking_matches_reference_golden(native, recordings, name, stage, vari
     if variant == "exact":
         scale = max(np.abs(ref[f]).max() for f in ("I_P", "Q_P", "I_E", "Q_E", "I_L", "Q_L"))
         for f in ("I_P", "I_E", "I_L", "Q_E", "Q_P", "Q_L"):
-            assert np.abs(got[f] - ref[f]).max() <= 1e-8 * scale, f
-        assert np.abs(got["carrFreq"] - ref["carrFreq"]).max() <= 1e-6
-        assert np.abs(got["codeFreq"] - ref["codeFreq"]).max() <= 1e-7
+            assert np.abs(got[f] - ref[f]).max() <= 1e-9 * scale, f
+        assert np.abs(got["carrFreq"] - ref["carrFreq"]).max() <= 1e-7
+        assert np.abs(got["codeFreq"] - ref["codeFreq"]).max() <= 1e-8
 
 
 def test_tracking_class_surface_and_file_object(native, recordings, tmp_path):
