@@ -604,10 +604,20 @@ __device__ __forceinline__ void correlate_exact(const MsParams& P, const int8_t*
         xi[d] = __dp4a((int)w, twi[d][q], xi[d]);
       }
     }
-    // exact recombination of the base-256 digits (|value| < 2^52, exact in float64)
-    double Sr = (double)xr[ND - 1], Si = (double)xi[ND - 1];
-#pragma unroll
-    for (int d = ND - 2; d >= 0; --d) { Sr = fma(Sr, 256.0, (double)xr[d]); Si = fma(Si, 256.0, (double)xi[d]); }
+    // exact recombination of the base-256 digits (|value| < 2^52, exact in float64); digit pairs are
+    // first merged in int32 (|x1*256 + x0| < 2^28) to halve the int->double conversions
+    double Sr, Si;
+    {
+      const int r01 = xr[1] * 256 + xr[0], i01 = xi[1] * 256 + xi[0];
+      const int r23 = xr[3] * 256 + xr[2], i23 = xi[3] * 256 + xi[2];
+      if (ND == 5) {
+        Sr = fma(fma((double)xr[4], 65536.0, (double)r23), 65536.0, (double)r01);
+        Si = fma(fma((double)xi[4], 65536.0, (double)i23), 65536.0, (double)i01);
+      } else {
+        Sr = fma((double)r23, 65536.0, (double)r01);
+        Si = fma((double)i23, 65536.0, (double)i01);
+      }
+    }
     const double Rr = rotr * Sr - roti * Si, Ri = rotr * Si + roti * Sr;
     aEr += sE * Rr; aEi += sE * Ri;
     aPr += sP * Rr; aPi += sP * Ri;
