@@ -54,6 +54,7 @@ struct TrackArgs {
 struct MsParams {
   double startE, stepE, startL, stepL, startP, stepP;  // np.linspace(start, ., blk, endpoint=False)
   double inv_step;  // 1/codePhaseStep, used only to *predict* event indices
+  long long q0_fix, h_fix;   // Q40 fixed point: predicted sample index of threshold n is (q0 + n*h) / 2^40
   double cps;       // carrier cycles per sample
   double rem_cyc;   // remCarrPhase in cycles
   double w;         // carrFreq * 2.0 * pi (tracking.py:195), rad/s
@@ -155,6 +156,8 @@ __device__ void prepare_code(const TrackArgs& a, CodeState& st, long long rec_le
   p.startP = rem;                                                     // :182
   p.stepP = ((bs + rem) - p.startP) / (double)blk;
   p.inv_step = 1.0 / step;
+  p.h_fix = __double2ll_rn(0.5 * p.inv_step * 1099511627776.0);
+  p.q0_fix = __double2ll_rn(-rem * p.inv_step * 1099511627776.0);
   st.nextRemCode = (lin_y(blk - 1, p.stepP, p.startP) + step) - 1023.0;  // :190
 }
 
@@ -510,20 +513,20 @@ __device__ __forceinline__ void correlate_exact(const MsParams& P, const int8_t*
   const int n0 = SEGS * tid - 1;
   int beta[SEGS + 1];
   bool irregular = false;
-  const double h = 0.5 * P.inv_step, q0 = -P.startP * P.inv_step;
+  // boundaries are equally spaced in the predicted (real-valued) sample index q_n = (n/2 - rem) / step;
+  // the prediction runs in Q40 fixed point (error < 1e-9 samples over the 2046 thresholds)
+  long long qf = P.q0_fix + (long long)n0 * P.h_fix;
+  const long long FR_ONE = 1LL << 40, FR_EPS = 1099512;   // 1e-6 in Q40
 #pragma unroll
-  for (int s = 0; s <= SEGS; ++s) {
+  for (int s = 0; s <= SEGS; ++s, qf += P.h_fix) {
     const int n = n0 + s;
     int b;
     if (n < 0) b = 0;
     else if (n > 2046) b = P.blk;
     else {
-      // boundaries are equally spaced in the predicted (real-valued) sample index: q_n = (n/2 - rem) / step
-      const double q = fma((double)n, h, q0);
-      const double fl = floor(q);
-      b = (int)fl + 1;
-      const double fr = q - fl;
-      if (fr < 1e-6 || fr > 1.0 - 1e-6) {   // too close to a sample instant: settle with the exact expressions
+      b = (int)(qf >> 40) + 1;
+      const long long fr = qf & (FR_ONE - 1);
+      if (fr < FR_EPS || fr > FR_ONE - FR_EPS) {   // too close to a sample instant: settle with the exact expressions
         if ((n & 1) == 0) b = next_event(n >> 1, P.startP, P.stepP, P.inv_step);
         else {
           const int c = (n - 1) >> 1;
@@ -572,63 +575,65 @@ __device__ __forceinline__ void correlate_exact(const MsParams& P, const int8_t*
   for (int s = 0; s < SEGS; ++s) {
     const int a = beta[s];
     const int b = beta[s + 1];
-    if (b <= a) continue;
-    const int n = n0 + s;
-    const double sP = codeD[(n >> 1) + 1];
-    const int ie = (n + 1) >> 1;
-    const double sE = codeD[ie], sL = codeD[ie + 1];
-    if (fresh) {
-      // the reference's own phase expression for sample a (tracking.py:193-195), evaluated in radians so
-      // that no rounded 1/(2 pi) scales a 6e4 rad argument (that error would be common to all threads)
-      sincos(P.w * ((double)a / P.fs) + P.rem_rad, &roti, &rotr);
-      fresh = false;
-    }
-    const int len = b - a;
-    const int addr = off + a;
-    const unsigned* wp = reinterpret_cast<const unsigned*>(cur + (addr & ~3));
-    const int sh = (addr & 3) * 8;
-    unsigned raw[NW + 1];
-#pragma unroll
-    for (int q = 0; q <= NW; ++q) raw[q] = wp[q];
-    int xr[ND], xi[ND];
-#pragma unroll
-    for (int d = 0; d < ND; ++d) { xr[d] = 0; xi[d] = 0; }
-#pragma unroll
-    for (int q = 0; q < NW; ++q) {
-      unsigned w = __funnelshift_r(raw[q], raw[q + 1], sh);
-      const int keep = len - 4 * q;
-      if (keep < 4) w &= keep <= 0 ? 0u : (0xFFFFFFFFu >> (8 * (4 - keep)));
-#pragma unroll
-      for (int d = 0; d < ND; ++d) {
-        xr[d] = __dp4a((int)w, twr[d][q], xr[d]);
-        xi[d] = __dp4a((int)w, twi[d][q], xi[d]);
+    if (b > a) {
+      const int n = n0 + s;
+      const double sP = codeD[(n >> 1) + 1];
+      const int ie = (n + 1) >> 1;
+      const double sE = codeD[ie], sL = codeD[ie + 1];
+      if (fresh) {
+        // the reference's own phase expression for sample a (tracking.py:193-195), evaluated in radians so
+        // that no rounded 1/(2 pi) scales a 6e4 rad argument (that error would be common to all threads)
+        sincos(P.w * ((double)a / P.fs) + P.rem_rad, &roti, &rotr);
+        fresh = false;
       }
-    }
-    // exact recombination of the base-256 digits (|value| < 2^52, exact in float64); digit pairs are
-    // first merged in int32 (|x1*256 + x0| < 2^28) to halve the int->double conversions
-    double Sr, Si;
-    {
-      const int r01 = xr[1] * 256 + xr[0], i01 = xi[1] * 256 + xi[0];
-      const int r23 = xr[3] * 256 + xr[2], i23 = xi[3] * 256 + xi[2];
-      if (ND == 5) {
-        Sr = fma(fma((double)xr[4], 65536.0, (double)r23), 65536.0, (double)r01);
-        Si = fma(fma((double)xi[4], 65536.0, (double)i23), 65536.0, (double)i01);
+      const int len = b - a;
+      const int sh = ((off + a) & 3) * 8;
+      unsigned raw[NW + 1];
+      {
+        const unsigned* wp = reinterpret_cast<const unsigned*>(cur + ((off + a) & ~3));
+#pragma unroll
+        for (int q = 0; q <= NW; ++q) raw[q] = wp[q];
+      }
+      int xr[ND], xi[ND];
+#pragma unroll
+      for (int d = 0; d < ND; ++d) { xr[d] = 0; xi[d] = 0; }
+#pragma unroll
+      for (int q = 0; q < NW; ++q) {
+        unsigned w = __funnelshift_r(raw[q], raw[q + 1], sh);
+        const int keep = len - 4 * q;
+        if (keep < 4) w &= keep <= 0 ? 0u : (0xFFFFFFFFu >> (8 * (4 - keep)));
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+          xr[d] = __dp4a((int)w, twr[d][q], xr[d]);
+          xi[d] = __dp4a((int)w, twi[d][q], xi[d]);
+        }
+      }
+      // exact recombination of the base-256 digits (|value| < 2^52, exact in float64); digit pairs are
+      // first merged in int32 (|x1*256 + x0| < 2^28) to halve the int->double conversions
+      double Sr, Si;
+      {
+        const int r01 = xr[1] * 256 + xr[0], i01 = xi[1] * 256 + xi[0];
+        const int r23 = xr[3] * 256 + xr[2], i23 = xi[3] * 256 + xi[2];
+        if (ND == 5) {
+          Sr = fma(fma((double)xr[4], 65536.0, (double)r23), 65536.0, (double)r01);
+          Si = fma(fma((double)xi[4], 65536.0, (double)i23), 65536.0, (double)i01);
+        } else {
+          Sr = fma((double)r23, 65536.0, (double)r01);
+          Si = fma((double)i23, 65536.0, (double)i01);
+        }
+      }
+      const double Rr = rotr * Sr - roti * Si, Ri = rotr * Si + roti * Sr;
+      aEr += sE * Rr; aEi += sE * Ri;
+      aPr += sP * Rr; aPi += sP * Ri;
+      aLr += sL * Rr; aLi += sL * Ri;
+      const int j = len - (LMAX - 4);
+      if (j >= 0) {
+        const double zr = T.z[j][0], zi = T.z[j][1];
+        const double nr = rotr * zr - roti * zi, ni = rotr * zi + roti * zr;
+        rotr = nr; roti = ni;
       } else {
-        Sr = fma((double)r23, 65536.0, (double)r01);
-        Si = fma((double)i23, 65536.0, (double)i01);
+        fresh = true;
       }
-    }
-    const double Rr = rotr * Sr - roti * Si, Ri = rotr * Si + roti * Sr;
-    aEr += sE * Rr; aEi += sE * Ri;
-    aPr += sP * Rr; aPi += sP * Ri;
-    aLr += sL * Rr; aLi += sL * Ri;
-    const int j = len - (LMAX - 4);
-    if (j >= 0) {
-      const double zr = T.z[j][0], zi = T.z[j][1];
-      const double nr = rotr * zr - roti * zi, ni = rotr * zi + roti * zr;
-      rotr = nr; roti = ni;
-    } else {
-      fresh = true;
     }
   }
   const double sc = 1.0 / (double)(1LL << (8 * ND - 2));   // 2^-30 or 2^-38
