@@ -45,6 +45,9 @@ struct TrackArgs {
   int* status;          // [R*C] sgx_status of the channel
   int n_channels;
   int ms;
+  int resume;           // continue every channel from `state` (streaming ingest: the recording arrives in chunks)
+  long long avail;      // bytes of every recording that are resident so far (>= rec_len when complete)
+  struct TrackState* state;  // [R*C]
   int win;              // bytes per staging buffer, multiple of 16
   long long skip;
   double fs, codeFreqBasis, codeLength, spc;
@@ -138,6 +141,15 @@ struct CarrState {   // tracking.py:118-122, :128-130
   double carrFreq, carrFreqBasis, remCarrPhase, oldCarrNco, oldCarrError, w;
 };
 
+constexpr int SGX_PAUSED = 1;   // MsParams.stop: the next block is not resident yet (streaming ingest)
+
+struct TrackState {   // loop state of one channel between two launches of a streamed recording
+  CodeState c;
+  CarrState r;
+  int k;        // periods completed
+  int status;   // SGX_OK (finished), SGX_PAUSED, or an error
+};
+
 // T3 + T4 parameters + T5 carry for the next period (code thread)
 __device__ void prepare_code(const TrackArgs& a, CodeState& st, long long rec_len, MsParams& p) {
   double step = st.codeFreq / a.fs;                                   // :148
@@ -147,6 +159,7 @@ __device__ void prepare_code(const TrackArgs& a, CodeState& st, long long rec_le
   p.stop = 0;
   long long aligned = st.pos & ~15LL;
   if (st.pos + blk > rec_len) { p.stop = SGX_ERR_SHORT; return; }     // :159
+  if (st.pos + blk > a.avail) { p.stop = SGX_PAUSED; return; }         // wait for the next chunk of the file
   if (blk <= 0 || (st.pos - aligned) + blk > a.win) { p.stop = SGX_ERR_RANGE; return; }
   double rem = st.remCodePhase, spc = a.spc, bs = (double)blk * step;
   p.startE = rem - spc;                                               // :166
@@ -657,7 +670,11 @@ __global__ void __launch_bounds__(TRK_THREADS, 2) track_kernel(TrackArgs a) {
   const int rid = cid / a.n_channels;
   const sgx_channel chn = a.ch[cid];
   if (chn.prn == 0) {  // tracking.py:99 -- idle channel, no record
-    if (tid == 0) { a.ms_done[cid] = 0; a.status[cid] = SGX_OK; }
+    if (tid == 0) {
+      a.ms_done[cid] = 0;
+      a.status[cid] = SGX_OK;
+      if (a.state) { a.state[cid].k = 0; a.state[cid].status = SGX_OK; }
+    }
     return;
   }
   const int8_t* rec = a.rec + (long long)rid * a.rec_stride;
@@ -672,20 +689,31 @@ __global__ void __launch_bounds__(TRK_THREADS, 2) track_kernel(TrackArgs a) {
   }
   CodeState cst;
   CarrState rst;
-  if (tid == 0) {
-    cst.codeFreq = a.codeFreqBasis;          // :114
-    cst.remCodePhase = 0.0;
-    cst.oldCodeNco = cst.oldCodeError = 0.0;
-    cst.pos = a.skip + (long long)chn.codePhase;  // :107
-    prepare_code(a, cst, rec_len, prm);
-    if (BULK) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); }
-  }
-  if (tid == 32) {
-    rst.carrFreq = chn.acquiredFreq;         // :118
-    rst.carrFreqBasis = chn.acquiredFreq;
-    rst.remCarrPhase = 0.0;
-    rst.oldCarrNco = rst.oldCarrError = 0.0;
-    prepare_carr(a, rst, prm);
+  int k_start = 0;
+  if (a.resume) {
+    const TrackState* ts = a.state + cid;
+    if (ts->status != SGX_PAUSED) return;   // finished (or failed) in an earlier launch
+    k_start = ts->k;
+    if (tid == 0) { cst = ts->c; prepare_code(a, cst, rec_len, prm); }
+    if (tid == 32) { rst = ts->r; prepare_carr(a, rst, prm); }
+    if (tid == 0 && BULK) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); }
+  } else {
+    if (tid == 0) {
+      cst.codeFreq = a.codeFreqBasis;          // :114
+      cst.remCodePhase = 0.0;
+      cst.oldCodeNco = cst.oldCodeError = 0.0;
+      cst.nextRemCode = 0.0;
+      cst.pos = a.skip + (long long)chn.codePhase;  // :107
+      prepare_code(a, cst, rec_len, prm);
+      if (BULK) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); }
+    }
+    if (tid == 32) {
+      rst.carrFreq = chn.acquiredFreq;         // :118
+      rst.carrFreqBasis = chn.acquiredFreq;
+      rst.remCarrPhase = 0.0;
+      rst.oldCarrNco = rst.oldCarrError = 0.0;
+      prepare_carr(a, rst, prm);
+    }
   }
   if (EXACT && (tid >> 5) == 1) {   // the carrier thread's warp builds the twiddle / rotor tables
     const double cps = __shfl_sync(0xffffffffu, tid == 32 ? prm.cps : 0.0, 0);
@@ -710,17 +738,18 @@ __global__ void __launch_bounds__(TRK_THREADS, 2) track_kernel(TrackArgs a) {
   };
   unsigned phase0 = 0, phase1 = 0;  // mbarrier phase parity per buffer
   bool pending0 = false, pending1 = false;
-  if (prm.stop == 0) {
-    int nb = stage(buf0, prm.pos);
+  if (prm.stop == 0) {   // window of the first period of this launch, into the buffer of its parity
+    const int par = k_start & 1;
+    int nb = stage(par ? buf1 : buf0, prm.pos);
     if (BULK) {
       if (nb > 0) {
-        if (tid == 0) bulk_load(buf0, rec + (prm.pos & ~15LL), (unsigned)nb, &mbar[0]);
-        pending0 = true;
+        if (tid == 0) bulk_load(par ? buf1 : buf0, rec + (prm.pos & ~15LL), (unsigned)nb, &mbar[par]);
+        if (par) pending1 = true; else pending0 = true;
       }
     }
   }
 
-  int k = 0;
+  int k = k_start;
   for (; k < a.ms; ++k) {
     const MsParams P = prm;
     if (P.stop != 0) break;
@@ -731,7 +760,7 @@ __global__ void __launch_bounds__(TRK_THREADS, 2) track_kernel(TrackArgs a) {
       if (k & 1) { if (pending1) { mbar_wait(&mbar[1], phase1); phase1 ^= 1; pending1 = false; } }
       else       { if (pending0) { mbar_wait(&mbar[0], phase0); phase0 ^= 1; pending0 = false; } }
     } else {
-      if (k == 0) { cp_async_wait_all(); __syncthreads(); }
+      if (k == k_start) { cp_async_wait_all(); __syncthreads(); }
     }
     // ---- prefetch the next period's window -------------------------------------------------
     {
@@ -803,14 +832,19 @@ __global__ void __launch_bounds__(TRK_THREADS, 2) track_kernel(TrackArgs a) {
     cp_async_wait_all();
   }
   if (tid == 0) {
+    const int status = (k == a.ms) ? SGX_OK : prm.stop;
     a.ms_done[cid] = k;
-    a.status[cid] = (k == a.ms) ? SGX_OK : prm.stop;
+    a.status[cid] = status;
+    if (a.state) { a.state[cid].c = cst; a.state[cid].k = k; a.state[cid].status = status; }
   }
+  if (tid == 32 && a.state) a.state[cid].r = rst;
 }
 
 // --------------------------------------------------------------------------- host entry
 struct TrackScratch {
-  DevBuf rec, len, ch, chips, out, done, status;
+  DevBuf rec, len, ch, chips, out, done, status, state;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
 };
 static TrackScratch g_trk;
 
@@ -840,21 +874,19 @@ extern "C" int sgx_track(const int8_t* rec, int64_t rec_stride, const int64_t* r
 
   const int8_t* d_rec = rec;
   long long stride = rec_stride;
-  if (!is_device_ptr(rec)) {  // host recording: stage it in HBM once (the np.fromfile replacement)
-    long long mx = 0;
-    for (int r = 0; r < n_recordings; ++r) mx = rec_len[r] > mx ? rec_len[r] : mx;
-    stride = (mx + 15) & ~15LL;
+  long long max_len = 0;
+  for (int r = 0; r < n_recordings; ++r) max_len = rec_len[r] > max_len ? rec_len[r] : max_len;
+  const bool host_input = !is_device_ptr(rec);
+  if (host_input) {  // host recording: it is streamed into HBM in chunks while tracking runs (np.fromfile replacement)
+    stride = (max_len + 15) & ~15LL;
     if (g_trk.rec.reserve((size_t)stride * n_recordings + 16)) return fail(SGX_ERR_CUDA, "cudaMalloc", "recording");
-    for (int r = 0; r < n_recordings; ++r)
-      SGX_CUDA(cudaMemcpyAsync(g_trk.rec.as<int8_t>() + (size_t)r * stride, rec + (size_t)r * rec_stride,
-                               (size_t)rec_len[r], cudaMemcpyHostToDevice, s));
     d_rec = g_trk.rec.as<int8_t>();
   } else if ((rec_stride & 15) || ((uintptr_t)rec & 15)) {
     return fail(SGX_ERR_ARG, "sgx_track", "device recordings must be 16-byte aligned with a stride multiple of 16");
   }
   if (g_trk.len.reserve(sizeof(long long) * n_recordings) || g_trk.ch.reserve(sizeof(sgx_channel) * nch) ||
       g_trk.chips.reserve(32 * 1023) || g_trk.done.reserve(sizeof(int) * nch) ||
-      g_trk.status.reserve(sizeof(int) * nch))
+      g_trk.status.reserve(sizeof(int) * nch) || g_trk.state.reserve(sizeof(TrackState) * nch))
     return fail(SGX_ERR_CUDA, "cudaMalloc", "tracking scratch");
   SGX_CUDA(cudaMemcpyAsync(g_trk.len.p, rec_len, sizeof(long long) * n_recordings, cudaMemcpyHostToDevice, s));
   SGX_CUDA(cudaMemcpyAsync(g_trk.ch.p, ch, sizeof(sgx_channel) * nch, cudaMemcpyHostToDevice, s));
@@ -878,6 +910,9 @@ extern "C" int sgx_track(const int8_t* rec, int64_t rec_stride, const int64_t* r
   a.status = g_trk.status.as<int>();
   a.n_channels = n_channels;
   a.ms = ms;
+  a.resume = 0;
+  a.avail = 0x7fffffffffffffffLL;
+  a.state = g_trk.state.as<TrackState>();
   a.win = win;
   a.skip = st->skipNumberOfBytes;
   a.fs = st->samplingFreq;
@@ -890,6 +925,7 @@ extern "C" int sgx_track(const int8_t* rec, int64_t rec_stride, const int64_t* r
   a.c2carr = st->PDIcarr / st->tau1carr;
 
   const size_t smem = 2 * (size_t)win;
+  auto launch = [&]() -> int {
   // correlate variant: half-chip segments when a segment fits the unrolled path, else aligned groups
   const double half_chip = st->samplingFreq / (2.0 * st->codeFreqBasis);   // samples per half chip
   int nw = ((int)ceil(half_chip + 0.25) + 3) / 4;
@@ -925,6 +961,38 @@ extern "C" int sgx_track(const int8_t* rec, int64_t rec_stride, const int64_t* r
   }
 #undef SGX_TRK_EXACT
 #undef SGX_TRK_GO
+    return SGX_OK;
+  };
+  if (!host_input) {
+    int rc0 = launch();
+    if (rc0) return rc0;
+  } else {
+    // Streamed ingest: chunk c of every recording is copied on a second stream while the kernel works on
+    // the periods whose samples are already resident; channels pause at the end of the resident data and
+    // are resumed by the next launch (TrackState).  With pageable host memory the copies simply serialise.
+    if (!g_trk.copy_stream) {
+      SGX_CUDA(cudaStreamCreateWithFlags(&g_trk.copy_stream, cudaStreamNonBlocking));
+      SGX_CUDA(cudaEventCreateWithFlags(&g_trk.ev[0], cudaEventDisableTiming));
+      SGX_CUDA(cudaEventCreateWithFlags(&g_trk.ev[1], cudaEventDisableTiming));
+    }
+    long long chunk = 1024LL * st->samplesPerCode;
+    if (const char* e = getenv("SGX_TRK_CHUNK_MS")) { if (atoll(e) > 0) chunk = atoll(e) * st->samplesPerCode; }
+    chunk = (chunk + 15) & ~15LL;
+    SGX_CUDA(cudaEventRecord(g_trk.ev[1], s));                     // the copy stream starts after earlier work on s
+    SGX_CUDA(cudaStreamWaitEvent(g_trk.copy_stream, g_trk.ev[1], 0));
+    int c = 0;
+    for (long long off = 0; off < max_len; off += chunk, ++c) {
+      const long long width = (max_len - off) < chunk ? (max_len - off) : chunk;
+      SGX_CUDA(cudaMemcpy2DAsync(g_trk.rec.as<int8_t>() + off, (size_t)stride, rec + off, (size_t)rec_stride, (size_t)width,
+                                 (size_t)n_recordings, cudaMemcpyHostToDevice, g_trk.copy_stream));
+      SGX_CUDA(cudaEventRecord(g_trk.ev[0], g_trk.copy_stream));
+      SGX_CUDA(cudaStreamWaitEvent(s, g_trk.ev[0], 0));
+      a.avail = off + width;
+      a.resume = c > 0;
+      int rc0 = launch();
+      if (rc0) return rc0;
+    }
+  }
   SGX_CUDA(cudaGetLastError());
   if (out_on_host) SGX_CUDA(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, s));
   int* h_status = (int*)malloc(sizeof(int) * nch);

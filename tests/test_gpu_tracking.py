@@ -148,3 +148,26 @@ def test_batch_device_resident_equals_single(native, recordings):
     assert np.array_equal(o[0], o[2])
     rc1, o1, _ = track_batch(host[:1, :n].copy(), [n], [ch], s)
     assert rc1 == 0 and np.array_equal(o1[0], o[0])
+
+
+@pytest.mark.parametrize("chunk_ms", ["1", "7", "64"])
+def test_streamed_ingest_equals_resident(native, recordings, chunk_ms, monkeypatch):
+    """Host recordings are copied to HBM in chunks while tracking runs; channels pause at the end of the
+    resident data and resume in the next launch.  The result must equal the device-resident run bit for
+    bit (same arithmetic, only the launch boundaries differ)."""
+    import torch
+    from softgnss_python_b200.tracking import track_batch
+    g = gold("trk_skip")
+    _, data = recordings["trk_skip"]
+    s = case_settings(CASES["trk_skip"])
+    ch = channels_from_gold(g)
+    n = data.size
+    stride = (n + 15) // 16 * 16
+    dev = torch.zeros((1, stride), dtype=torch.int8, device="cuda")
+    dev[0, :n] = torch.from_numpy(data).cuda()
+    rc0, out0, done0 = track_batch(dev, [n], [ch], s)
+    monkeypatch.setenv("SGX_TRK_CHUNK_MS", chunk_ms)
+    rc1, out1, done1 = track_batch(data.reshape(1, -1), [n], [ch], s)
+    assert rc0 == 0 and rc1 == 0 and np.array_equal(done0, done1)
+    act = [i for i in range(len(ch.PRN)) if ch.PRN[i] != 0]
+    assert np.array_equal(out0[0, act], out1[0, act])

@@ -359,13 +359,27 @@ static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return 0; }
 static inline cudaError_t cudaSetDevice(int) { return 0; }
 static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return 0; }
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { memset(p, 0, sizeof(*p)); p->multiProcessorCount = 8; strcpy(p->name, "cpu-emul"); p->major = 10; return 0; }
-static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void*) { a->type = cudaMemoryTypeDevice; a->device = 0; return 0; }
+static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void*) {
+  // SGX_EMUL_HOST=1 makes every caller buffer look like host memory, which exercises the staging paths
+  a->type = getenv("SGX_EMUL_HOST") ? cudaMemoryTypeUnregistered : cudaMemoryTypeDevice;
+  a->device = 0;
+  return 0;
+}
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return 0; }
 static inline cudaError_t cudaEventCreate(cudaEvent_t*) { return 0; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = 0) { return 0; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
 static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0; return 0; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }
+enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2 };
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (cudaStream_t)1; return 0; }
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = (cudaEvent_t)1; return 0; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return 0; }
+static inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, cudaMemcpyKind,
+                                            cudaStream_t = 0) {
+  for (size_t r = 0; r < h; ++r) memcpy((char*)d + r * dp, (const char*)s + r * sp, w);
+  return 0;
+}
 
 #define SGX_LAUNCH(kernel, grid, block, smem, stream, ...) \
   sgx_emul::launch((grid), (block), (smem), [&]() { kernel(__VA_ARGS__); })
