@@ -663,6 +663,8 @@ __global__ void __launch_bounds__(TRK_THREADS, 2) track_kernel(TrackArgs a) {
   __shared__ float codeS[1040];  // 1025 used; the tail absorbs indices reached only by masked samples
   __shared__ unsigned long long mbar[2];
   __shared__ ExactTables xt;
+  __shared__ CodeState cstS;   // loop state lives in shared memory: only threads 0 / 32 touch it, and keeping it
+  __shared__ CarrState rstS;   // out of the register file leaves the correlator loop without spills
   __shared__ double codeD[EXACT ? 1040 : 1];
 
   const int tid = threadIdx.x;
@@ -687,32 +689,34 @@ __global__ void __launch_bounds__(TRK_THREADS, 2) track_kernel(TrackArgs a) {
       if (EXACT) codeD[i] = (double)codeS[i];
     }
   }
-  CodeState cst;
-  CarrState rst;
   int k_start = 0;
   if (a.resume) {
     const TrackState* ts = a.state + cid;
     if (ts->status != SGX_PAUSED) return;   // finished (or failed) in an earlier launch
     k_start = ts->k;
-    if (tid == 0) { cst = ts->c; prepare_code(a, cst, rec_len, prm); }
-    if (tid == 32) { rst = ts->r; prepare_carr(a, rst, prm); }
+    if (tid == 0) { CodeState c = ts->c; prepare_code(a, c, rec_len, prm); cstS = c; }
+    if (tid == 32) { CarrState r = ts->r; prepare_carr(a, r, prm); rstS = r; }
     if (tid == 0 && BULK) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); }
   } else {
     if (tid == 0) {
-      cst.codeFreq = a.codeFreqBasis;          // :114
-      cst.remCodePhase = 0.0;
-      cst.oldCodeNco = cst.oldCodeError = 0.0;
-      cst.nextRemCode = 0.0;
-      cst.pos = a.skip + (long long)chn.codePhase;  // :107
-      prepare_code(a, cst, rec_len, prm);
+      CodeState c;
+      c.codeFreq = a.codeFreqBasis;          // :114
+      c.remCodePhase = 0.0;
+      c.oldCodeNco = c.oldCodeError = 0.0;
+      c.nextRemCode = 0.0;
+      c.pos = a.skip + (long long)chn.codePhase;  // :107
+      prepare_code(a, c, rec_len, prm);
+      cstS = c;
       if (BULK) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); }
     }
     if (tid == 32) {
-      rst.carrFreq = chn.acquiredFreq;         // :118
-      rst.carrFreqBasis = chn.acquiredFreq;
-      rst.remCarrPhase = 0.0;
-      rst.oldCarrNco = rst.oldCarrError = 0.0;
-      prepare_carr(a, rst, prm);
+      CarrState r;
+      r.carrFreq = chn.acquiredFreq;         // :118
+      r.carrFreqBasis = chn.acquiredFreq;
+      r.remCarrPhase = 0.0;
+      r.oldCarrNco = r.oldCarrError = 0.0;
+      prepare_carr(a, r, prm);
+      rstS = r;
     }
   }
   if (EXACT && (tid >> 5) == 1) {   // the carrier thread's warp builds the twiddle / rotor tables
@@ -786,6 +790,7 @@ __global__ void __launch_bounds__(TRK_THREADS, 2) track_kernel(TrackArgs a) {
     if (!BULK) cp_async_wait_all();
     __syncthreads();
     if (tid == 0) {          // ---- code thread: DLL (tracking.py:238-251), T5, T3/T4 of the next period
+      CodeState cst = cstS;
       double I_E = 0.0, Q_E = 0.0, I_L = 0.0, Q_L = 0.0;
       for (int w = 0; w < TRK_WARPS; ++w) { I_E += red[w][0]; Q_E += red[w][1]; I_L += red[w][4]; Q_L += red[w][5]; }
       cst.remCodePhase = cst.nextRemCode;
@@ -803,7 +808,9 @@ __global__ void __launch_bounds__(TRK_THREADS, 2) track_kernel(TrackArgs a) {
       o[1 * m] = cst.codeFreq;
       o[4 * m] = I_E; o[5 * m] = I_L; o[6 * m] = Q_E; o[8 * m] = Q_L;
       o[9 * m] = codeError; o[10 * m] = codeNco;
+      cstS = cst;
     } else if (tid == 32) {  // ---- carrier thread: T6 carry, PLL (tracking.py:223-235), T6 of the next period
+      CarrState rst = rstS;
       double I_P = 0.0, Q_P = 0.0;
       for (int w = 0; w < TRK_WARPS; ++w) { I_P += red[w][2]; Q_P += red[w][3]; }
       rst.remCarrPhase = carry_carr_phase(a, rst, P.blk);
@@ -818,6 +825,7 @@ __global__ void __launch_bounds__(TRK_THREADS, 2) track_kernel(TrackArgs a) {
       o[2 * m] = rst.carrFreq;
       o[3 * m] = I_P; o[7 * m] = Q_P;
       o[11 * m] = carrError; o[12 * m] = carrNco;
+      rstS = rst;
     }
     if (EXACT && (tid >> 5) == 1 && k + 1 < a.ms) {
       const double cps = __shfl_sync(0xffffffffu, tid == 32 ? prm.cps : 0.0, 0);
@@ -835,9 +843,9 @@ __global__ void __launch_bounds__(TRK_THREADS, 2) track_kernel(TrackArgs a) {
     const int status = (k == a.ms) ? SGX_OK : prm.stop;
     a.ms_done[cid] = k;
     a.status[cid] = status;
-    if (a.state) { a.state[cid].c = cst; a.state[cid].k = k; a.state[cid].status = status; }
+    if (a.state) { a.state[cid].c = cstS; a.state[cid].k = k; a.state[cid].status = status; }
   }
-  if (tid == 32 && a.state) a.state[cid].r = rst;
+  if (tid == 32 && a.state) a.state[cid].r = rstS;
 }
 
 // --------------------------------------------------------------------------- host entry
