@@ -48,6 +48,7 @@ struct TrackArgs {
   int resume;           // continue every channel from `state` (streaming ingest: the recording arrives in chunks)
   long long avail;      // bytes of every recording that are resident so far (>= rec_len when complete)
   struct TrackState* state;  // [R*C]
+  long long* prof;      // optional [R*C][4] cycle counters (SGX_TRK_PROF=1): correlate, reduce+barrier, bookkeeping, barrier
   int win;              // bytes per staging buffer, multiple of 16
   long long skip;
   double fs, codeFreqBasis, codeLength, spc;
@@ -481,6 +482,39 @@ struct ExactTables {
   double z[5][2];             // rotor steps e^{j 2 pi (LMAX-4+j) cps}
 };
 
+// Branch-free float64 sin/cos for |th| < 5e5 rad: three-term Cody-Waite reduction by pi/2 (33-bit
+// pieces, k < 2^19 so every k*piece is exact) and Taylor polynomials on [-pi/4, pi/4]; max error
+// 2.3e-16 over [0, 7e4] (checked against libm).  Straight-line code, so it overlaps with the integer
+// work around it instead of stalling the warp like the library routine's branches do.
+__device__ __forceinline__ void sincos_reduced(double th, double& sn, double& cs) {
+  const double k = rint(th * 0.6366197723675814);
+  double r = fma(-k, 1.5707963267341256, th);
+  r = fma(-k, 6.077100506303966e-11, r);
+  r = fma(-k, 2.0222662487959506e-21, r);
+  const double r2 = r * r;
+  double ps = -7.647163731819816e-13;                 // -1/15!
+  ps = fma(ps, r2, 1.6059043836821613e-10);           //  1/13!
+  ps = fma(ps, r2, -2.505210838544172e-08);           // -1/11!
+  ps = fma(ps, r2, 2.7557319223985893e-06);           //  1/9!
+  ps = fma(ps, r2, -1.984126984126984e-04);           // -1/7!
+  ps = fma(ps, r2, 8.333333333333333e-03);            //  1/5!
+  ps = fma(ps, r2, -1.6666666666666666e-01);          // -1/3!
+  const double s0 = fma(ps * r2, r, r);
+  double pc = 4.779477332387385e-14;                  //  1/16!
+  pc = fma(pc, r2, -1.1470745597729725e-11);          // -1/14!
+  pc = fma(pc, r2, 2.08767569878681e-09);             //  1/12!
+  pc = fma(pc, r2, -2.755731922398589e-07);           // -1/10!
+  pc = fma(pc, r2, 2.48015873015873e-05);             //  1/8!
+  pc = fma(pc, r2, -1.388888888888889e-03);           // -1/6!
+  pc = fma(pc, r2, 4.1666666666666664e-02);           //  1/4!
+  pc = fma(pc, r2, -0.5);
+  const double c0 = fma(pc, r2, 1.0);
+  const int q = (int)(long long)k & 3;
+  const double sa = (q & 1) ? c0 : s0, ca = (q & 1) ? s0 : c0;
+  sn = (q & 2) ? -sa : sa;
+  cs = ((q + 1) & 2) ? -ca : ca;
+}
+
 __device__ __forceinline__ void cis_cycles_f64(double cyc, double& c, double& s) {
   cyc -= rint(cyc);
   sincospi(2.0 * cyc, &s, &c);
@@ -516,12 +550,68 @@ __device__ __forceinline__ void build_exact_tables(ExactTables& T, double cps, i
   }
 }
 
-template <int NW>
-__device__ __forceinline__ void correlate_exact(const MsParams& P, const int8_t* cur, const double* codeD,
-                                                const ExactTables& T, int tid, double& tEr, double& tEi,
+// ---- cold paths of the exact correlator, kept out of line: the unrolled segment loop has to stay inside the SM's
+// instruction cache (with these inlined eight times the kernel was 115 KB of SASS and instruction fetch from the
+// GPC-level cache ran at 88 % of its peak -- profiles/ncu_summary_r1_v3.md)
+__device__ __noinline__ int settle_boundary(int n, const MsParams& P, bool& irregular) {
+  if ((n & 1) == 0) return next_event(n >> 1, P.startP, P.stepP, P.inv_step);
+  const int c = (n - 1) >> 1;
+  const int b = next_event(c, P.startE, P.stepE, P.inv_step);
+  if (next_event(c + 1, P.startL, P.stepL, P.inv_step) != b) irregular = true;
+  return b;
+}
+
+__device__ __noinline__ void start_rotor(int a, const MsParams& P, double& sn, double& cs) {
+  // the reference's own phase expression for sample a (tracking.py:193-195), evaluated in radians so that no
+  // rounded 1/(2 pi) scales a 6e4 rad argument (that error would be common to all threads)
+  const double th = P.w * ((double)a / P.fs) + P.rem_rad;
+  if (fabs(th) < 5.0e5) sincos_reduced(th, sn, cs);
+  else sincos(th, &sn, &cs);
+}
+
+__device__ __noinline__ void correlate_per_sample(const MsParams& P, const int8_t* cur, const unsigned char* codeB, int off,
+                                                  int i0, int i1, double* acc) {
+  // exact per-sample evaluation (tracking.py:166-219 verbatim, float64)
+  for (int i = i0; i < i1; ++i) {
+    const int ie = (int)ceil(lin_y(i, P.stepE, P.startE));
+    const int ip = (int)ceil(lin_y(i, P.stepP, P.startP));
+    const int il = (int)ceil(lin_y(i, P.stepL, P.startL));
+    double cs, sn;
+    cis_cycles_f64((double)i * P.cps + P.rem_cyc, cs, sn);
+    const double x = (double)cur[off + i];
+    const double pr = x * cs, pi = x * sn;
+    const double ce = codeB[ie] ? -1.0 : 1.0, cp = codeB[ip] ? -1.0 : 1.0, cl = codeB[il] ? -1.0 : 1.0;
+    acc[0] += ce * pr; acc[1] += ce * pi;
+    acc[2] += cp * pr; acc[3] += cp * pi;
+    acc[4] += cl * pr; acc[5] += cl * pi;
+  }
+}
+
+__device__ long long* g_fine_prof = nullptr;   // SGX_TRK_PROF=2: [8] cycle counters of thread 64 of block 0 inside correlate_exact
+
+// +-x without a multiply: the code value's sign bit (0 / 0x80000000) is XORed into the high word
+__device__ __forceinline__ double flip_sign(double x, unsigned m) {
+  return __hiloint2double(__double2hiint(x) ^ (int)m, __double2loint(x));
+}
+
+// exact double of the 46-bit integer lo + mid*2^16 + hi*2^32 (|value| < 2^51) without an int->double conversion
+// instruction: the integer, offset by 2^51, is written straight into the mantissa of 2^52 and the offset removed by
+// one exact subtraction
+__device__ __forceinline__ double digits_to_double(int lo, int mid, int hi) {
+  long long v = (long long)mid * 65536 + (long long)lo;
+  v += (long long)hi << 32;
+  v += 0x4338000000000000LL;            // 2^52 exponent pattern, plus the 2^51 offset inside the mantissa
+  return __longlong_as_double(v) - 6755399441055744.0;   // 2^52 + 2^51
+}
+
+template <int NW, int SEGS>
+__device__ __forceinline__ void correlate_exact(const MsParams& P, const MsParams& Pcold, const int8_t* cur,
+                                                const unsigned char* codeB, const ExactTables& T, int tid, double& tEr, double& tEi,
                                                 double& tPr, double& tPi, double& tLr, double& tLi) {
-  constexpr int SEGS = 8;
   constexpr int LMAX = 4 * NW;
+  const bool probe = g_fine_prof != nullptr && tid == 64 && blockIdx.x == 0;
+  long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+  if (probe) c0 = clock64();
   const int off = (int)(P.pos - (P.pos & ~15LL));
   const int n0 = SEGS * tid - 1;
   int beta[SEGS + 1];
@@ -540,13 +630,7 @@ __device__ __forceinline__ void correlate_exact(const MsParams& P, const int8_t*
       b = (int)(qf >> 40) + 1;
       const long long fr = qf & (FR_ONE - 1);
       if (fr < FR_EPS || fr > FR_ONE - FR_EPS) {   // too close to a sample instant: settle with the exact expressions
-        if ((n & 1) == 0) b = next_event(n >> 1, P.startP, P.stepP, P.inv_step);
-        else {
-          const int c = (n - 1) >> 1;
-          b = next_event(c, P.startE, P.stepE, P.inv_step);
-          const int bl = next_event(c + 1, P.startL, P.stepL, P.inv_step);
-          if (bl != b) irregular = true;
-        }
+        b = settle_boundary(n, Pcold, irregular);   // (Pcold: the shared-memory copy, so P can stay in registers)
       }
     }
     beta[s] = max(0, min(b, P.blk));   // (a prediction of -1 occurs when rem is within rounding of one step)
@@ -556,21 +640,12 @@ __device__ __forceinline__ void correlate_exact(const MsParams& P, const int8_t*
 #pragma unroll
   for (int s = 0; s < SEGS; ++s) too_long = too_long || (beta[s + 1] - beta[s] > LMAX);
   if (irregular || too_long) {
-    // exact per-sample evaluation (tracking.py:166-219 verbatim, float64)
-    for (int i = beta[0]; i < beta[SEGS]; ++i) {
-      const int ie = (int)ceil(lin_y(i, P.stepE, P.startE));
-      const int ip = (int)ceil(lin_y(i, P.stepP, P.startP));
-      const int il = (int)ceil(lin_y(i, P.stepL, P.startL));
-      double cs, sn;
-      cis_cycles_f64((double)i * P.cps + P.rem_cyc, cs, sn);
-      const double x = (double)cur[off + i];
-      const double pr = x * cs, pi = x * sn;
-      tEr += codeD[ie] * pr; tEi += codeD[ie] * pi;
-      tPr += codeD[ip] * pr; tPi += codeD[ip] * pi;
-      tLr += codeD[il] * pr; tLi += codeD[il] * pi;
-    }
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    correlate_per_sample(Pcold, cur, codeB, off, beta[0], beta[SEGS], acc);
+    tEr += acc[0]; tEi += acc[1]; tPr += acc[2]; tPi += acc[3]; tLr += acc[4]; tLi += acc[5];
     return;
   }
+  if (probe) c1 = clock64();
   // packed twiddle digits: tw[c][d] word q holds samples 4q .. 4q+3
   constexpr int ND = ExactDigits<NW>::value;
   int twr[ND][NW], twi[ND][NW];
@@ -581,22 +656,28 @@ __device__ __forceinline__ void correlate_exact(const MsParams& P, const int8_t*
       twr[d][q] = reinterpret_cast<const int*>(T.tw[0][d])[q];
       twi[d][q] = reinterpret_cast<const int*>(T.tw[1][d])[q];
     }
+  // code signs of the SEGS/2 + 1 chips this thread's segments touch (chip (SEGS/2)*tid onwards), one byte each
+  // (0 = +1, 0x80 = -1): two conflict-free aligned words instead of three float64 table reads per segment
+  static_assert(SEGS == 8, "sign bytes are fetched for 8 half-chip segments per thread");
+  const unsigned sg_lo = reinterpret_cast<const unsigned*>(codeB)[tid];       // chips 4 tid .. 4 tid + 3
+  const unsigned sg_hi = reinterpret_cast<const unsigned*>(codeB)[tid + 1];   // chip 4 tid + 4 in its low byte
+  auto sign_of = [&](int j) -> unsigned {   // j = chip index - 4 tid, a compile-time constant after unrolling
+    return j < 3 ? (sg_lo << (24 - 8 * j)) & 0x80000000u : j == 3 ? sg_lo & 0x80000000u : (sg_hi << 24) & 0x80000000u;
+  };
   double rotr = 1.0, roti = 0.0;
   double aEr = 0, aEi = 0, aPr = 0, aPi = 0, aLr = 0, aLi = 0;
   bool fresh = true;
+  if (probe) c2 = clock64();
 #pragma unroll
   for (int s = 0; s < SEGS; ++s) {
     const int a = beta[s];
     const int b = beta[s + 1];
+    if (probe && s == 1) c3 = clock64();
     if (b > a) {
-      const int n = n0 + s;
-      const double sP = codeD[(n >> 1) + 1];
-      const int ie = (n + 1) >> 1;
-      const double sE = codeD[ie], sL = codeD[ie + 1];
+      // chips relative to 4 tid: P = floor((s-1)/2) + 1, E = floor(s/2), L = E + 1  (n = 8 tid - 1 + s)
+      const unsigned mP = sign_of((s + 1) >> 1), mE = sign_of(s >> 1), mL = sign_of((s >> 1) + 1);
       if (fresh) {
-        // the reference's own phase expression for sample a (tracking.py:193-195), evaluated in radians so
-        // that no rounded 1/(2 pi) scales a 6e4 rad argument (that error would be common to all threads)
-        sincos(P.w * ((double)a / P.fs) + P.rem_rad, &roti, &rotr);
+        start_rotor(a, Pcold, roti, rotr);
         fresh = false;
       }
       const int len = b - a;
@@ -607,65 +688,67 @@ __device__ __forceinline__ void correlate_exact(const MsParams& P, const int8_t*
 #pragma unroll
         for (int q = 0; q <= NW; ++q) raw[q] = wp[q];
       }
+      // bytes at and beyond len are not part of this segment: the last word is always masked, the others only in
+      // a short segment (fewer than LMAX - 4 samples: block edges)
+      unsigned w[NW];
+#pragma unroll
+      for (int q = 0; q < NW; ++q) w[q] = __funnelshift_r(raw[q], raw[q + 1], sh);
+      w[NW - 1] &= __funnelshift_lc(0xFFFFFFFFu, 0u, max(8 * (len - 4 * (NW - 1)), 0));
+      if (len < LMAX - 4) {
+#pragma unroll
+        for (int q = 0; q < NW - 1; ++q) w[q] &= __funnelshift_lc(0xFFFFFFFFu, 0u, max(8 * (len - 4 * q), 0));
+      }
       int xr[ND], xi[ND];
 #pragma unroll
       for (int d = 0; d < ND; ++d) { xr[d] = 0; xi[d] = 0; }
 #pragma unroll
       for (int q = 0; q < NW; ++q) {
-        unsigned w = __funnelshift_r(raw[q], raw[q + 1], sh);
-        const int keep = len - 4 * q;
-        if (keep < 4) w &= keep <= 0 ? 0u : (0xFFFFFFFFu >> (8 * (4 - keep)));
 #pragma unroll
         for (int d = 0; d < ND; ++d) {
-          xr[d] = __dp4a((int)w, twr[d][q], xr[d]);
-          xi[d] = __dp4a((int)w, twi[d][q], xi[d]);
+          xr[d] = __dp4a((int)w[q], twr[d][q], xr[d]);
+          xi[d] = __dp4a((int)w[q], twi[d][q], xi[d]);
         }
       }
-      // exact recombination of the base-256 digits (|value| < 2^52, exact in float64); digit pairs are
-      // first merged in int32 (|x1*256 + x0| < 2^28) to halve the int->double conversions
-      double Sr, Si;
-      {
-        const int r01 = xr[1] * 256 + xr[0], i01 = xi[1] * 256 + xi[0];
-        const int r23 = xr[3] * 256 + xr[2], i23 = xi[3] * 256 + xi[2];
-        if (ND == 5) {
-          Sr = fma(fma((double)xr[4], 65536.0, (double)r23), 65536.0, (double)r01);
-          Si = fma(fma((double)xi[4], 65536.0, (double)i23), 65536.0, (double)i01);
-        } else {
-          Sr = fma((double)r23, 65536.0, (double)r01);
-          Si = fma((double)i23, 65536.0, (double)i01);
-        }
-      }
-      const double Rr = rotr * Sr - roti * Si, Ri = rotr * Si + roti * Sr;
-      aEr += sE * Rr; aEi += sE * Ri;
-      aPr += sP * Rr; aPi += sP * Ri;
-      aLr += sL * Rr; aLi += sL * Ri;
+      // exact recombination of the base-256 digits (|value| < 2^51): digit pairs merge in int32
+      // (|x1*256 + x0| < 2^28), the rest in int64, and the result goes straight into a float64 mantissa
+      const double Sr = digits_to_double(xr[1] * 256 + xr[0], xr[3] * 256 + xr[2], ND == 5 ? xr[ND - 1] : 0);
+      const double Si = digits_to_double(xi[1] * 256 + xi[0], xi[3] * 256 + xi[2], ND == 5 ? xi[ND - 1] : 0);
+      const double Rr = fma(rotr, Sr, -(roti * Si)), Ri = fma(rotr, Si, roti * Sr);
+      aEr += flip_sign(Rr, mE); aEi += flip_sign(Ri, mE);
+      aPr += flip_sign(Rr, mP); aPi += flip_sign(Ri, mP);
+      aLr += flip_sign(Rr, mL); aLi += flip_sign(Ri, mL);
       const int j = len - (LMAX - 4);
       if (j >= 0) {
         const double zr = T.z[j][0], zi = T.z[j][1];
-        const double nr = rotr * zr - roti * zi, ni = rotr * zi + roti * zr;
+        const double nr = fma(rotr, zr, -(roti * zi)), ni = fma(rotr, zi, roti * zr);
         rotr = nr; roti = ni;
       } else {
         fresh = true;
       }
     }
   }
+  if (probe) {
+    const long long c4 = clock64();
+    g_fine_prof[0] += c1 - c0; g_fine_prof[1] += c2 - c1; g_fine_prof[2] += c3 - c2; g_fine_prof[3] += c4 - c3; g_fine_prof[4] += 1;
+  }
   const double sc = 1.0 / (double)(1LL << (8 * ND - 2));   // 2^-30 or 2^-38
   tEr += aEr * sc; tEi += aEi * sc; tPr += aPr * sc; tPi += aPi * sc; tLr += aLr * sc; tLi += aLi * sc;
 }
 
-template <bool BULK, int NW, bool EXACT>
-__global__ void __launch_bounds__(TRK_THREADS, 2) track_kernel(TrackArgs a) {
+template <bool BULK, int NW, bool EXACT, int NT>
+__global__ void __launch_bounds__(NT, 2) track_kernel(TrackArgs a) {
   SGX_DYN_SMEM(smem);
   int8_t* buf0 = (int8_t*)smem;
   int8_t* buf1 = buf0 + a.win;
   __shared__ MsParams prm;
-  __shared__ double red[TRK_WARPS][6];
+  constexpr int NWARPS = NT / 32;
+  __shared__ double red[NWARPS][6];
   __shared__ float codeS[1040];  // 1025 used; the tail absorbs indices reached only by masked samples
   __shared__ unsigned long long mbar[2];
   __shared__ ExactTables xt;
   __shared__ CodeState cstS;   // loop state lives in shared memory: only threads 0 / 32 touch it, and keeping it
   __shared__ CarrState rstS;   // out of the register file leaves the correlator loop without spills
-  __shared__ double codeD[EXACT ? 1040 : 1];
+  __shared__ __align__(4) unsigned char codeB[EXACT ? 1040 : 4];   // code sign bytes: 0 = +1, 0x80 = -1
 
   const int tid = threadIdx.x;
   const int cid = blockIdx.x;  // recording * n_channels + channel
@@ -684,9 +767,9 @@ __global__ void __launch_bounds__(TRK_THREADS, 2) track_kernel(TrackArgs a) {
   const long long rec_alloc = (rec_len + 15) & ~15LL;
   {  // padded code [c1022, c0..c1022, c0] (tracking.py:109-111)
     const int8_t* c = a.chips + (chn.prn - 1) * 1023;
-    for (int i = tid; i < 1040; i += TRK_THREADS) {
+    for (int i = tid; i < 1040; i += NT) {
       codeS[i] = i < 1025 ? (float)c[(i + 1022) % 1023] : 0.f;
-      if (EXACT) codeD[i] = (double)codeS[i];
+      if (EXACT) codeB[i] = codeS[i] < 0.f ? 0x80 : 0;
     }
   }
   int k_start = 0;
@@ -735,7 +818,7 @@ __global__ void __launch_bounds__(TRK_THREADS, 2) track_kernel(TrackArgs a) {
       return (int)nb;
     } else {
       const int8_t* src = rec + al;
-      for (int o = tid * 16; o < (int)nb; o += TRK_THREADS * 16) cp_async16(dst + o, src + o);
+      for (int o = tid * 16; o < (int)nb; o += NT * 16) cp_async16(dst + o, src + o);
       cp_async_commit();
       return (int)nb;
     }
@@ -757,6 +840,8 @@ __global__ void __launch_bounds__(TRK_THREADS, 2) track_kernel(TrackArgs a) {
   for (; k < a.ms; ++k) {
     const MsParams P = prm;
     if (P.stop != 0) break;
+    long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+    if (a.prof && (tid == 0 || tid == 64)) t0 = clock64();
     int8_t* cur = (k & 1) ? buf1 : buf0;
     int8_t* nxt = (k & 1) ? buf0 : buf1;
     // ---- make this period's samples visible ------------------------------------------------
@@ -766,6 +851,7 @@ __global__ void __launch_bounds__(TRK_THREADS, 2) track_kernel(TrackArgs a) {
     } else {
       if (k == k_start) { cp_async_wait_all(); __syncthreads(); }
     }
+    if (g_fine_prof && a.prof && tid == 64 && blockIdx.x == 0) g_fine_prof[5] += clock64() - t0;
     // ---- prefetch the next period's window -------------------------------------------------
     {
       long long npos = P.pos + P.blk;
@@ -776,11 +862,13 @@ __global__ void __launch_bounds__(TRK_THREADS, 2) track_kernel(TrackArgs a) {
       }
     }
 
+    if (g_fine_prof && a.prof && tid == 64 && blockIdx.x == 0) g_fine_prof[6] += clock64() - t0;
     double tEr = 0.0, tEi = 0.0, tPr = 0.0, tPi = 0.0, tLr = 0.0, tLi = 0.0;
-    if (EXACT)       correlate_exact<(NW > 0 ? NW : 1)>(P, cur, codeD, xt, tid, tEr, tEi, tPr, tPi, tLr, tLi);
+    if (EXACT)       correlate_exact<(NW > 0 ? NW : 1), 2048 / NT>(P, prm, cur, codeB, xt, tid, tEr, tEi, tPr, tPi, tLr, tLi);
     else if (NW > 0) correlate_segments<(NW > 0 ? NW : 1)>(P, cur, codeS, tid, tEr, tEi, tPr, tPi, tLr, tLi);
     else             correlate_groups(P, cur, codeS, tid, tEr, tEi, tPr, tPi, tLr, tLi);
     // I arm = sin (imaginary part), Q arm = cos (real part): tracking.py:205-207
+    if (a.prof && (tid == 0 || tid == 64)) t1 = clock64();
     double v0 = warp_sum_f64(tEi), v1 = warp_sum_f64(tEr), v2 = warp_sum_f64(tPi), v3 = warp_sum_f64(tPr),
            v4 = warp_sum_f64(tLi), v5 = warp_sum_f64(tLr);
     if ((tid & 31) == 0) {
@@ -789,10 +877,11 @@ __global__ void __launch_bounds__(TRK_THREADS, 2) track_kernel(TrackArgs a) {
     }
     if (!BULK) cp_async_wait_all();
     __syncthreads();
+    if (a.prof && (tid == 0 || tid == 64)) t2 = clock64();
     if (tid == 0) {          // ---- code thread: DLL (tracking.py:238-251), T5, T3/T4 of the next period
       CodeState cst = cstS;
       double I_E = 0.0, Q_E = 0.0, I_L = 0.0, Q_L = 0.0;
-      for (int w = 0; w < TRK_WARPS; ++w) { I_E += red[w][0]; Q_E += red[w][1]; I_L += red[w][4]; Q_L += red[w][5]; }
+      for (int w = 0; w < NWARPS; ++w) { I_E += red[w][0]; Q_E += red[w][1]; I_L += red[w][4]; Q_L += red[w][5]; }
       cst.remCodePhase = cst.nextRemCode;
       cst.pos = P.pos + P.blk;
       double em = sqrt(I_E * I_E + Q_E * Q_E), lm = sqrt(I_L * I_L + Q_L * Q_L);
@@ -812,7 +901,7 @@ __global__ void __launch_bounds__(TRK_THREADS, 2) track_kernel(TrackArgs a) {
     } else if (tid == 32) {  // ---- carrier thread: T6 carry, PLL (tracking.py:223-235), T6 of the next period
       CarrState rst = rstS;
       double I_P = 0.0, Q_P = 0.0;
-      for (int w = 0; w < TRK_WARPS; ++w) { I_P += red[w][2]; Q_P += red[w][3]; }
+      for (int w = 0; w < NWARPS; ++w) { I_P += red[w][2]; Q_P += red[w][3]; }
       rst.remCarrPhase = carry_carr_phase(a, rst, P.blk);
       double carrError = atan(Q_P / I_P) * 0.5 / 3.141592653589793;   // x/2.0 == x*0.5 exactly
       double carrNco = rst.oldCarrNco + a.c1carr * (carrError - rst.oldCarrError) + carrError * a.c2carr;
@@ -831,7 +920,13 @@ __global__ void __launch_bounds__(TRK_THREADS, 2) track_kernel(TrackArgs a) {
       const double cps = __shfl_sync(0xffffffffu, tid == 32 ? prm.cps : 0.0, 0);
       build_exact_tables<(NW > 0 ? NW : 1)>(xt, cps, tid & 31);
     }
+    if (a.prof && tid == 0) t3 = clock64();
     __syncthreads();
+    if (a.prof && (tid == 0 || tid == 64)) {
+      const long long t4 = clock64();
+      long long* pr = a.prof + (long long)cid * 8 + (tid == 0 ? 0 : 4);
+      pr[0] += t1 - t0; pr[1] += t2 - t1; pr[2] += (tid == 0 ? t3 - t2 : 0); pr[3] += t4 - (tid == 0 ? t3 : t2);
+    }
   }
   if (BULK) {  // never exit with a bulk copy in flight
     if (pending0) mbar_wait(&mbar[0], phase0);
@@ -850,11 +945,12 @@ __global__ void __launch_bounds__(TRK_THREADS, 2) track_kernel(TrackArgs a) {
 
 // --------------------------------------------------------------------------- host entry
 struct TrackScratch {
-  DevBuf rec, len, ch, chips, out, done, status, state;
+  DevBuf rec, len, ch, chips, out, done, status, state, prof;
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev[2] = {nullptr, nullptr};
 };
 static TrackScratch g_trk;
+static long long* g_fine_host = nullptr;
 
 static bool use_bulk() {
   const char* e = getenv("SGX_TRK_STAGE");
@@ -921,6 +1017,20 @@ extern "C" int sgx_track(const int8_t* rec, int64_t rec_stride, const int64_t* r
   a.resume = 0;
   a.avail = 0x7fffffffffffffffLL;
   a.state = g_trk.state.as<TrackState>();
+  a.prof = nullptr;
+  if (getenv("SGX_TRK_PROF")) {
+    if (g_trk.prof.reserve(sizeof(long long) * 8 * nch)) return fail(SGX_ERR_CUDA, "cudaMalloc", "prof");
+    SGX_CUDA(cudaMemsetAsync(g_trk.prof.p, 0, sizeof(long long) * 8 * nch, s));
+    a.prof = g_trk.prof.as<long long>();
+    if (atoi(getenv("SGX_TRK_PROF")) == 2) {
+      static DevBuf fine;
+      if (fine.reserve(64)) return fail(SGX_ERR_CUDA, "cudaMalloc", "fine prof");
+      SGX_CUDA(cudaMemsetAsync(fine.p, 0, 64, s));
+      long long* fp = fine.as<long long>();
+      SGX_CUDA(cudaMemcpyToSymbolAsync(g_fine_prof, &fp, sizeof(fp), 0, cudaMemcpyHostToDevice, s));
+      g_fine_host = fp;
+    }
+  }
   a.win = win;
   a.skip = st->skipNumberOfBytes;
   a.fs = st->samplingFreq;
@@ -944,12 +1054,13 @@ extern "C" int sgx_track(const int8_t* rec, int64_t rec_stride, const int64_t* r
   }
   if (fabs(st->dllCorrelatorSpacing - 0.5) > 1e-12) nw = 0;                 // segment scheme assumes E/L at +-0.5 chip
   const bool bulk = use_bulk();
-#define SGX_TRK_GO(B, W, X)                                                                        \
+#define SGX_TRK_GO_NT(B, W, X, NTHR)                                                               \
   {                                                                                                \
-    auto kfn = track_kernel<B, W, X>;                                                              \
+    auto kfn = track_kernel<B, W, X, NTHR>;                                                        \
     SGX_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-    SGX_COUNTED_LAUNCH(kfn, dim3(nch), dim3(TRK_THREADS), smem, s, a);                             \
+    SGX_COUNTED_LAUNCH(kfn, dim3(nch), dim3(NTHR), smem, s, a);                                    \
   }
+#define SGX_TRK_GO(B, W, X) SGX_TRK_GO_NT(B, W, X, TRK_THREADS)
 #define SGX_TRK_EXACT(W) { if (bulk) SGX_TRK_GO(true, W, true) else SGX_TRK_GO(false, W, true) }
   if (nw >= 1 && nw <= 8 && exact) {
     switch (nw) {
@@ -969,6 +1080,7 @@ extern "C" int sgx_track(const int8_t* rec, int64_t rec_stride, const int64_t* r
   }
 #undef SGX_TRK_EXACT
 #undef SGX_TRK_GO
+#undef SGX_TRK_GO_NT
     return SGX_OK;
   };
   if (!host_input) {
@@ -1007,6 +1119,22 @@ extern "C" int sgx_track(const int8_t* rec, int64_t rec_stride, const int64_t* r
   SGX_CUDA(cudaMemcpyAsync(ms_done, a.ms_done, sizeof(int) * nch, cudaMemcpyDeviceToHost, s));
   SGX_CUDA(cudaMemcpyAsync(h_status, a.status, sizeof(int) * nch, cudaMemcpyDeviceToHost, s));
   SGX_CUDA(cudaStreamSynchronize(s));
+  if (a.prof && g_fine_host) {
+    long long f[8];
+    cudaMemcpy(f, g_fine_host, 64, cudaMemcpyDeviceToHost);
+    if (f[4] > 0) fprintf(stderr, "[sgx prof] thread 64 inside correlate, cycles/period: boundaries %.0f tables %.0f first segment (incl. start rotor) %.0f other segments %.0f | before: window wait %.0f, +prefetch issue %.0f\n",
+                          (double)f[0] / f[4], (double)f[1] / f[4], (double)f[2] / f[4], (double)f[3] / f[4], (double)f[5] / f[4], (double)f[6] / f[4]);
+  }
+  if (a.prof) {
+    long long* hp = (long long*)malloc(sizeof(long long) * 8 * nch);
+    cudaMemcpy(hp, a.prof, sizeof(long long) * 8 * nch, cudaMemcpyDeviceToHost);
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < nch; ++i) for (int j = 0; j < 8; ++j) acc[j] += (double)hp[i * 8 + j];
+    const double per = (double)nch * ms;
+    fprintf(stderr, "[sgx prof] cycles/period thread0: correlate %.0f reduce+bar %.0f bookkeeping %.0f bar %.0f | thread64: correlate %.0f reduce+bar %.0f wait-for-bookkeeping %.0f\n",
+            acc[0] / per, acc[1] / per, acc[2] / per, acc[3] / per, acc[4] / per, acc[5] / per, acc[7] / per);
+    free(hp);
+  }
   int rc = SGX_OK;
   for (int i = 0; i < nch; ++i)
     if (h_status[i] != SGX_OK && rc == SGX_OK) rc = h_status[i];

@@ -31,7 +31,7 @@
 #define __launch_bounds__(...)
 #define __shared__ static thread_local
 #define __constant__ static
-#define __align__(n) alignas(n)
+#define __align__(n) __attribute__((aligned(n)))
 
 struct dim3 {
   unsigned x, y, z;
@@ -292,6 +292,11 @@ static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned s) {
 static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) {
   return (unsigned)(((((unsigned long long)hi) << 32) | lo) >> (sh & 31));
 }
+static inline unsigned __funnelshift_lc(unsigned lo, unsigned hi, unsigned sh) { if (sh > 32) sh = 32; unsigned long long v = ((unsigned long long)hi << 32) | lo; return sh == 32 ? lo : (unsigned)((v << sh) >> 32); }
+static inline int __double2hiint(double x) { long long v; memcpy(&v, &x, 8); return (int)(v >> 32); }
+static inline int __double2loint(double x) { long long v; memcpy(&v, &x, 8); return (int)(v & 0xffffffffLL); }
+static inline double __hiloint2double(int hi, int lo) { long long v = ((long long)hi << 32) | (unsigned)lo; double x; memcpy(&x, &v, 8); return x; }
+static inline double __longlong_as_double(long long v) { double x; memcpy(&x, &v, 8); return x; }
 static inline int __dp4a(int a, int b, int c) {
   for (int i = 0; i < 4; ++i) c += (int)(signed char)((a >> (8 * i)) & 0xFF) * (int)(signed char)((b >> (8 * i)) & 0xFF);
   return c;
@@ -330,6 +335,7 @@ static inline int atomicMin(int* p, int v) {
 static inline int atomicExch(int* p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_RELAXED); }
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline void __threadfence_block() {}
+static inline long long clock64() { return 0; }
 
 // ---- runtime API stubs -----------------------------------------------------------------------
 typedef int cudaError_t;
@@ -351,6 +357,7 @@ static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cuda
 static inline cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return 0; }
 static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = 0) { memset(d, v, n); return 0; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+template <class T> static inline cudaError_t cudaMemcpyToSymbolAsync(T& sym, const void* src, size_t n, size_t, cudaMemcpyKind, cudaStream_t = 0) { memcpy(&sym, src, n); return 0; }
 static inline cudaError_t cudaDeviceSynchronize() { return 0; }
 static inline cudaError_t cudaGetLastError() { return 0; }
 static inline cudaError_t cudaPeekAtLastError() { return 0; }
