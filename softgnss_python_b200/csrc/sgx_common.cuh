@@ -101,6 +101,39 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned coun
   asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
 #endif
 }
+// ---- explicit shared-window loads --------------------------------------------------------------------------
+// A 32-bit shared-window address taken once (smem_addr) and used with ld.shared keeps the compiler from
+// rematerialising the window base (S2R SR_CgaCtaId + LEA on sm_100) in front of every access inside a hot loop.
+// The generic pointer travels along for the CPU emulator build.
+__device__ __forceinline__ unsigned smem_addr(const void* p) {
+#ifdef SGX_EMUL
+  (void)p; return 0u;
+#else
+  // (made opaque, so the value is kept in its register instead of being recomputed at every use)
+  unsigned a = (unsigned)__cvta_generic_to_shared(p), o;
+  asm volatile("mov.u32 %0, %1;" : "=r"(o) : "r"(a));
+  return o;
+#endif
+}
+__device__ __forceinline__ unsigned lds_u32(const void* base, unsigned base_s, int byte_off) {
+#ifdef SGX_EMUL
+  (void)base_s; return *reinterpret_cast<const unsigned*>(reinterpret_cast<const char*>(base) + byte_off);
+#else
+  (void)base; unsigned v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base_s + (unsigned)byte_off));
+  return v;
+#endif
+}
+__device__ __forceinline__ double2 lds_f64x2(const void* base, unsigned base_s, int byte_off) {   // 16-byte aligned
+#ifdef SGX_EMUL
+  (void)base_s; return *reinterpret_cast<const double2*>(reinterpret_cast<const char*>(base) + byte_off);
+#else
+  (void)base; double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(base_s + (unsigned)byte_off));
+  return v;
+#endif
+}
+
 // one thread: arm the barrier with the byte count and start the copy (bytes % 16 == 0, both 16B-aligned)
 __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, unsigned bytes,
                                           unsigned long long* bar) {

@@ -477,7 +477,7 @@ __device__ __forceinline__ void correlate_segments(const MsParams& P, const int8
 // output ~5e-11), which keeps the carried code phase within ~1e-11 chips of the reference's and makes
 // chip reassignments a once-per-many-minutes event instead of a per-second one.
 template <int NW> struct ExactDigits { static constexpr int value = NW <= 5 ? 5 : 4; };   // Q38 twiddles when registers allow, else Q30
-struct ExactTables {
+struct __align__(16) ExactTables {
   signed char tw[2][5][32];   // [re/im][digit][k], read as packed words
   double z[5][2];             // rotor steps e^{j 2 pi (LMAX-4+j) cps}
 };
@@ -553,20 +553,24 @@ __device__ __forceinline__ void build_exact_tables(ExactTables& T, double cps, i
 // ---- cold paths of the exact correlator, kept out of line: the unrolled segment loop has to stay inside the SM's
 // instruction cache (with these inlined eight times the kernel was 115 KB of SASS and instruction fetch from the
 // GPC-level cache ran at 88 % of its peak -- profiles/ncu_summary_r1_v3.md)
-__device__ __noinline__ int settle_boundary(int n, const MsParams& P, bool& irregular) {
-  if ((n & 1) == 0) return next_event(n >> 1, P.startP, P.stepP, P.inv_step);
+// (results come back by value: an output reference would pin the caller's loop-carried state in local memory)
+constexpr int IRREGULAR = 1 << 30;   // flag on a settled boundary: E and L switch at different samples there
+__device__ __noinline__ int settle_boundary(int n, const MsParams& P) {
+  if ((n & 1) == 0) return max(0, min(next_event(n >> 1, P.startP, P.stepP, P.inv_step), P.blk));
   const int c = (n - 1) >> 1;
   const int b = next_event(c, P.startE, P.stepE, P.inv_step);
-  if (next_event(c + 1, P.startL, P.stepL, P.inv_step) != b) irregular = true;
-  return b;
+  const int bl = next_event(c + 1, P.startL, P.stepL, P.inv_step);
+  return max(0, min(b, P.blk)) | (bl != b ? IRREGULAR : 0);
 }
 
-__device__ __noinline__ void start_rotor(int a, const MsParams& P, double& sn, double& cs) {
+__device__ __noinline__ double2 start_rotor(int a, const MsParams& P) {   // (cos, sin)
   // the reference's own phase expression for sample a (tracking.py:193-195), evaluated in radians so that no
   // rounded 1/(2 pi) scales a 6e4 rad argument (that error would be common to all threads)
   const double th = P.w * ((double)a / P.fs) + P.rem_rad;
+  double sn, cs;
   if (fabs(th) < 5.0e5) sincos_reduced(th, sn, cs);
   else sincos(th, &sn, &cs);
+  return make_double2(cs, sn);
 }
 
 __device__ __noinline__ void correlate_per_sample(const MsParams& P, const int8_t* cur, const unsigned char* codeB, int off,
@@ -587,8 +591,6 @@ __device__ __noinline__ void correlate_per_sample(const MsParams& P, const int8_
   }
 }
 
-__device__ long long* g_fine_prof = nullptr;   // SGX_TRK_PROF=2: [8] cycle counters of thread 64 of block 0 inside correlate_exact
-
 // +-x without a multiply: the code value's sign bit (0 / 0x80000000) is XORed into the high word
 __device__ __forceinline__ double flip_sign(double x, unsigned m) {
   return __hiloint2double(__double2hiint(x) ^ (int)m, __double2loint(x));
@@ -604,50 +606,37 @@ __device__ __forceinline__ double digits_to_double(int lo, int mid, int hi) {
   return __longlong_as_double(v) - 6755399441055744.0;   // 2^52 + 2^51
 }
 
+// Exact correlator.  Thread tid walks the SEGS half-chip segments n = SEGS*tid - 1 ... in a ROLLED loop: one copy
+// of the segment body (about 170 instructions) instead of eight keeps the whole period loop inside the SM's
+// instruction cache (the unrolled kernel fetched instructions from the GPC-level cache at 88 % of that cache's
+// peak and stalled on it -- profiles/ncu_summary_r1_v3.md).
 template <int NW, int SEGS>
 __device__ __forceinline__ void correlate_exact(const MsParams& P, const MsParams& Pcold, const int8_t* cur,
-                                                const unsigned char* codeB, const ExactTables& T, int tid, double& tEr, double& tEi,
-                                                double& tPr, double& tPi, double& tLr, double& tLi) {
+                                                const unsigned char* codeB, const ExactTables& T, int tid,
+                                                double& tEr, double& tEi, double& tPr, double& tPi, double& tLr,
+                                                double& tLi) {
   constexpr int LMAX = 4 * NW;
-  const bool probe = g_fine_prof != nullptr && tid == 64 && blockIdx.x == 0;
-  long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-  if (probe) c0 = clock64();
+  constexpr int ND = ExactDigits<NW>::value;
+  static_assert(SEGS == 8, "sign bytes are fetched for 8 half-chip segments per thread");
   const int off = (int)(P.pos - (P.pos & ~15LL));
   const int n0 = SEGS * tid - 1;
-  int beta[SEGS + 1];
-  bool irregular = false;
   // boundaries are equally spaced in the predicted (real-valued) sample index q_n = (n/2 - rem) / step;
   // the prediction runs in Q40 fixed point (error < 1e-9 samples over the 2046 thresholds)
-  long long qf = P.q0_fix + (long long)n0 * P.h_fix;
   const long long FR_ONE = 1LL << 40, FR_EPS = 1099512;   // 1e-6 in Q40
-#pragma unroll
-  for (int s = 0; s <= SEGS; ++s, qf += P.h_fix) {
-    const int n = n0 + s;
-    int b;
-    if (n < 0) b = 0;
-    else if (n > 2046) b = P.blk;
-    else {
-      b = (int)(qf >> 40) + 1;
-      const long long fr = qf & (FR_ONE - 1);
-      if (fr < FR_EPS || fr > FR_ONE - FR_EPS) {   // too close to a sample instant: settle with the exact expressions
-        b = settle_boundary(n, Pcold, irregular);   // (Pcold: the shared-memory copy, so P can stay in registers)
-      }
-    }
-    beta[s] = max(0, min(b, P.blk));   // (a prediction of -1 occurs when rem is within rounding of one step)
-  }
-  if (beta[0] >= P.blk) return;
-  bool too_long = false;
-#pragma unroll
-  for (int s = 0; s < SEGS; ++s) too_long = too_long || (beta[s + 1] - beta[s] > LMAX);
-  if (irregular || too_long) {
-    double acc[6] = {0, 0, 0, 0, 0, 0};
-    correlate_per_sample(Pcold, cur, codeB, off, beta[0], beta[SEGS], acc);
-    tEr += acc[0]; tEi += acc[1]; tPr += acc[2]; tPi += acc[3]; tLr += acc[4]; tLi += acc[5];
-    return;
-  }
-  if (probe) c1 = clock64();
+  long long qf = P.q0_fix + (long long)n0 * P.h_fix;
+  // boundary of threshold n -> first sample of segment n, with IRREGULAR possibly set
+  auto boundary = [&](int n, long long q) -> int {
+    if (n < 0) return 0;
+    if (n > 2046) return P.blk;
+    const long long fr = q & (FR_ONE - 1);
+    // too close to a sample instant: settle with the exact expressions (Pcold: the shared-memory copy of the
+    // parameters, so that P can stay in registers)
+    if (fr < FR_EPS || fr > FR_ONE - FR_EPS) return settle_boundary(n, Pcold);
+    return max(0, min((int)(q >> 40) + 1, P.blk));   // (a prediction of -1 occurs when rem is within rounding of one step)
+  };
+  int a = boundary(n0, qf);
+  if ((a & ~IRREGULAR) >= P.blk) return;
   // packed twiddle digits: tw[c][d] word q holds samples 4q .. 4q+3
-  constexpr int ND = ExactDigits<NW>::value;
   int twr[ND][NW], twi[ND][NW];
 #pragma unroll
   for (int d = 0; d < ND; ++d)
@@ -656,80 +645,86 @@ __device__ __forceinline__ void correlate_exact(const MsParams& P, const MsParam
       twr[d][q] = reinterpret_cast<const int*>(T.tw[0][d])[q];
       twi[d][q] = reinterpret_cast<const int*>(T.tw[1][d])[q];
     }
-  // code signs of the SEGS/2 + 1 chips this thread's segments touch (chip (SEGS/2)*tid onwards), one byte each
-  // (0 = +1, 0x80 = -1): two conflict-free aligned words instead of three float64 table reads per segment
-  static_assert(SEGS == 8, "sign bytes are fetched for 8 half-chip segments per thread");
-  const unsigned sg_lo = reinterpret_cast<const unsigned*>(codeB)[tid];       // chips 4 tid .. 4 tid + 3
-  const unsigned sg_hi = reinterpret_cast<const unsigned*>(codeB)[tid + 1];   // chip 4 tid + 4 in its low byte
-  auto sign_of = [&](int j) -> unsigned {   // j = chip index - 4 tid, a compile-time constant after unrolling
-    return j < 3 ? (sg_lo << (24 - 8 * j)) & 0x80000000u : j == 3 ? sg_lo & 0x80000000u : (sg_hi << 24) & 0x80000000u;
-  };
+  // code signs of the 5 chips this thread's segments touch (chip 4*tid onwards), one byte each (0 = +1, 0x80 = -1):
+  // two conflict-free aligned words per period instead of three float64 table reads per segment
+  unsigned sg_lo = reinterpret_cast<const unsigned*>(codeB)[tid];       // chips 4 tid .. 4 tid + 3
+  unsigned sg_hi = reinterpret_cast<const unsigned*>(codeB)[tid + 1];   // chip 4 tid + 4 in its low byte
   double rotr = 1.0, roti = 0.0;
   double aEr = 0, aEi = 0, aPr = 0, aPi = 0, aLr = 0, aLi = 0;
   bool fresh = true;
-  if (probe) c2 = clock64();
-#pragma unroll
+  const unsigned cur_s = smem_addr(cur), z_s = smem_addr(&T.z[0][0]);
+#pragma unroll 1
   for (int s = 0; s < SEGS; ++s) {
-    const int a = beta[s];
-    const int b = beta[s + 1];
-    if (probe && s == 1) c3 = clock64();
-    if (b > a) {
-      // chips relative to 4 tid: P = floor((s-1)/2) + 1, E = floor(s/2), L = E + 1  (n = 8 tid - 1 + s)
-      const unsigned mP = sign_of((s + 1) >> 1), mE = sign_of(s >> 1), mL = sign_of((s >> 1) + 1);
-      if (fresh) {
-        start_rotor(a, Pcold, roti, rotr);
-        fresh = false;
-      }
-      const int len = b - a;
-      const int sh = ((off + a) & 3) * 8;
-      unsigned raw[NW + 1];
-      {
-        const unsigned* wp = reinterpret_cast<const unsigned*>(cur + ((off + a) & ~3));
+    qf += P.h_fix;
+    const int b = boundary(n0 + s + 1, qf);
+    const int len = (b & ~IRREGULAR) - (a & ~IRREGULAR);
+    if (len > 0) {
+      if (len > LMAX || ((a | b) & IRREGULAR)) {
+        // rare: a segment longer than the twiddle table, or one whose boundary is not shared by E, P and L.
+        // Per-sample evaluation; its sums join the scaled accumulators through an exact power of two.
+        double acc[6] = {0, 0, 0, 0, 0, 0};
+        correlate_per_sample(Pcold, cur, codeB, off, a & ~IRREGULAR, b & ~IRREGULAR, acc);
+        const double up = (double)(1LL << (8 * ND - 2));
+        aEr += acc[0] * up; aEi += acc[1] * up; aPr += acc[2] * up; aPi += acc[3] * up; aLr += acc[4] * up; aLi += acc[5] * up;
+        fresh = true;
+      } else {
+        // chips relative to 4 tid: E = floor(s/2), L = E + 1, P = floor((s+1)/2) = E (s even) or L (s odd)
+        // (n = 8 tid - 1 + s); the sign bytes are shifted down by one chip after every odd s
+        const unsigned mE = sg_lo << 24, mL = __byte_perm(sg_lo, 0u, 0x1444), mP = (s & 1) ? mL : mE;
+        if (fresh) {
+          const double2 r0 = start_rotor(a, Pcold);
+          rotr = r0.x; roti = r0.y;
+          fresh = false;
+        }
+        const int sh = ((off + a) & 3) * 8;
+        unsigned raw[NW + 1];
+        {
+          const int wo = (off + a) & ~3;
 #pragma unroll
-        for (int q = 0; q <= NW; ++q) raw[q] = wp[q];
-      }
-      // bytes at and beyond len are not part of this segment: the last word is always masked, the others only in
-      // a short segment (fewer than LMAX - 4 samples: block edges)
-      unsigned w[NW];
+          for (int q = 0; q <= NW; ++q) raw[q] = lds_u32(cur, cur_s, wo + 4 * q);
+        }
+        // bytes at and beyond len are not part of this segment: the last word is always masked, the others only
+        // in a short segment (fewer than LMAX - 4 samples: block edges)
+        unsigned w[NW];
 #pragma unroll
-      for (int q = 0; q < NW; ++q) w[q] = __funnelshift_r(raw[q], raw[q + 1], sh);
-      w[NW - 1] &= __funnelshift_lc(0xFFFFFFFFu, 0u, max(8 * (len - 4 * (NW - 1)), 0));
-      if (len < LMAX - 4) {
+        for (int q = 0; q < NW; ++q) w[q] = __funnelshift_r(raw[q], raw[q + 1], sh);
+        w[NW - 1] &= __funnelshift_lc(0xFFFFFFFFu, 0u, max(8 * (len - 4 * (NW - 1)), 0));
+        if (len < LMAX - 4) {
 #pragma unroll
-        for (int q = 0; q < NW - 1; ++q) w[q] &= __funnelshift_lc(0xFFFFFFFFu, 0u, max(8 * (len - 4 * q), 0));
-      }
-      int xr[ND], xi[ND];
+          for (int q = 0; q < NW - 1; ++q) w[q] &= __funnelshift_lc(0xFFFFFFFFu, 0u, max(8 * (len - 4 * q), 0));
+        }
+        int xr[ND], xi[ND];
 #pragma unroll
-      for (int d = 0; d < ND; ++d) { xr[d] = 0; xi[d] = 0; }
+        for (int d = 0; d < ND; ++d) { xr[d] = 0; xi[d] = 0; }
 #pragma unroll
-      for (int q = 0; q < NW; ++q) {
+        for (int q = 0; q < NW; ++q) {
 #pragma unroll
-        for (int d = 0; d < ND; ++d) {
-          xr[d] = __dp4a((int)w[q], twr[d][q], xr[d]);
-          xi[d] = __dp4a((int)w[q], twi[d][q], xi[d]);
+          for (int d = 0; d < ND; ++d) {
+            xr[d] = __dp4a((int)w[q], twr[d][q], xr[d]);
+            xi[d] = __dp4a((int)w[q], twi[d][q], xi[d]);
+          }
+        }
+        // exact recombination of the base-256 digits (|value| < 2^51): digit pairs merge in int32
+        // (|x1*256 + x0| < 2^28), the rest in int64, and the result goes straight into a float64 mantissa
+        const double Sr = digits_to_double(xr[1] * 256 + xr[0], xr[3] * 256 + xr[2], ND == 5 ? xr[ND - 1] : 0);
+        const double Si = digits_to_double(xi[1] * 256 + xi[0], xi[3] * 256 + xi[2], ND == 5 ? xi[ND - 1] : 0);
+        const double Rr = fma(rotr, Sr, -(roti * Si)), Ri = fma(rotr, Si, roti * Sr);
+        aEr += flip_sign(Rr, mE); aEi += flip_sign(Ri, mE);
+        aPr += flip_sign(Rr, mP); aPi += flip_sign(Ri, mP);
+        aLr += flip_sign(Rr, mL); aLi += flip_sign(Ri, mL);
+        const int j = len - (LMAX - 4);
+        if (j >= 0) {
+          const double2 z = lds_f64x2(&T.z[0][0], z_s, 16 * j);
+          const double zr = z.x, zi = z.y;
+          const double nr = fma(rotr, zr, -(roti * zi)), ni = fma(rotr, zi, roti * zr);
+          rotr = nr; roti = ni;
+        } else {
+          fresh = true;
         }
       }
-      // exact recombination of the base-256 digits (|value| < 2^51): digit pairs merge in int32
-      // (|x1*256 + x0| < 2^28), the rest in int64, and the result goes straight into a float64 mantissa
-      const double Sr = digits_to_double(xr[1] * 256 + xr[0], xr[3] * 256 + xr[2], ND == 5 ? xr[ND - 1] : 0);
-      const double Si = digits_to_double(xi[1] * 256 + xi[0], xi[3] * 256 + xi[2], ND == 5 ? xi[ND - 1] : 0);
-      const double Rr = fma(rotr, Sr, -(roti * Si)), Ri = fma(rotr, Si, roti * Sr);
-      aEr += flip_sign(Rr, mE); aEi += flip_sign(Ri, mE);
-      aPr += flip_sign(Rr, mP); aPi += flip_sign(Ri, mP);
-      aLr += flip_sign(Rr, mL); aLi += flip_sign(Ri, mL);
-      const int j = len - (LMAX - 4);
-      if (j >= 0) {
-        const double zr = T.z[j][0], zi = T.z[j][1];
-        const double nr = fma(rotr, zr, -(roti * zi)), ni = fma(rotr, zi, roti * zr);
-        rotr = nr; roti = ni;
-      } else {
-        fresh = true;
-      }
     }
-  }
-  if (probe) {
-    const long long c4 = clock64();
-    g_fine_prof[0] += c1 - c0; g_fine_prof[1] += c2 - c1; g_fine_prof[2] += c3 - c2; g_fine_prof[3] += c4 - c3; g_fine_prof[4] += 1;
+    a = b;
+    if (s & 1) { sg_lo = __funnelshift_r(sg_lo, sg_hi, 8); sg_hi >>= 8; }
   }
   const double sc = 1.0 / (double)(1LL << (8 * ND - 2));   // 2^-30 or 2^-38
   tEr += aEr * sc; tEi += aEi * sc; tPr += aPr * sc; tPi += aPi * sc; tLr += aLr * sc; tLi += aLi * sc;
@@ -851,7 +846,6 @@ __global__ void __launch_bounds__(NT, 2) track_kernel(TrackArgs a) {
     } else {
       if (k == k_start) { cp_async_wait_all(); __syncthreads(); }
     }
-    if (g_fine_prof && a.prof && tid == 64 && blockIdx.x == 0) g_fine_prof[5] += clock64() - t0;
     // ---- prefetch the next period's window -------------------------------------------------
     {
       long long npos = P.pos + P.blk;
@@ -862,7 +856,6 @@ __global__ void __launch_bounds__(NT, 2) track_kernel(TrackArgs a) {
       }
     }
 
-    if (g_fine_prof && a.prof && tid == 64 && blockIdx.x == 0) g_fine_prof[6] += clock64() - t0;
     double tEr = 0.0, tEi = 0.0, tPr = 0.0, tPi = 0.0, tLr = 0.0, tLi = 0.0;
     if (EXACT)       correlate_exact<(NW > 0 ? NW : 1), 2048 / NT>(P, prm, cur, codeB, xt, tid, tEr, tEi, tPr, tPi, tLr, tLi);
     else if (NW > 0) correlate_segments<(NW > 0 ? NW : 1)>(P, cur, codeS, tid, tEr, tEi, tPr, tPi, tLr, tLi);
@@ -950,7 +943,6 @@ struct TrackScratch {
   cudaEvent_t ev[2] = {nullptr, nullptr};
 };
 static TrackScratch g_trk;
-static long long* g_fine_host = nullptr;
 
 static bool use_bulk() {
   const char* e = getenv("SGX_TRK_STAGE");
@@ -1022,14 +1014,6 @@ extern "C" int sgx_track(const int8_t* rec, int64_t rec_stride, const int64_t* r
     if (g_trk.prof.reserve(sizeof(long long) * 8 * nch)) return fail(SGX_ERR_CUDA, "cudaMalloc", "prof");
     SGX_CUDA(cudaMemsetAsync(g_trk.prof.p, 0, sizeof(long long) * 8 * nch, s));
     a.prof = g_trk.prof.as<long long>();
-    if (atoi(getenv("SGX_TRK_PROF")) == 2) {
-      static DevBuf fine;
-      if (fine.reserve(64)) return fail(SGX_ERR_CUDA, "cudaMalloc", "fine prof");
-      SGX_CUDA(cudaMemsetAsync(fine.p, 0, 64, s));
-      long long* fp = fine.as<long long>();
-      SGX_CUDA(cudaMemcpyToSymbolAsync(g_fine_prof, &fp, sizeof(fp), 0, cudaMemcpyHostToDevice, s));
-      g_fine_host = fp;
-    }
   }
   a.win = win;
   a.skip = st->skipNumberOfBytes;
@@ -1119,12 +1103,6 @@ extern "C" int sgx_track(const int8_t* rec, int64_t rec_stride, const int64_t* r
   SGX_CUDA(cudaMemcpyAsync(ms_done, a.ms_done, sizeof(int) * nch, cudaMemcpyDeviceToHost, s));
   SGX_CUDA(cudaMemcpyAsync(h_status, a.status, sizeof(int) * nch, cudaMemcpyDeviceToHost, s));
   SGX_CUDA(cudaStreamSynchronize(s));
-  if (a.prof && g_fine_host) {
-    long long f[8];
-    cudaMemcpy(f, g_fine_host, 64, cudaMemcpyDeviceToHost);
-    if (f[4] > 0) fprintf(stderr, "[sgx prof] thread 64 inside correlate, cycles/period: boundaries %.0f tables %.0f first segment (incl. start rotor) %.0f other segments %.0f | before: window wait %.0f, +prefetch issue %.0f\n",
-                          (double)f[0] / f[4], (double)f[1] / f[4], (double)f[2] / f[4], (double)f[3] / f[4], (double)f[5] / f[4], (double)f[6] / f[4]);
-  }
   if (a.prof) {
     long long* hp = (long long*)malloc(sizeof(long long) * 8 * nch);
     cudaMemcpy(hp, a.prof, sizeof(long long) * 8 * nch, cudaMemcpyDeviceToHost);

@@ -293,6 +293,7 @@ static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) {
   return (unsigned)(((((unsigned long long)hi) << 32) | lo) >> (sh & 31));
 }
 static inline unsigned __funnelshift_lc(unsigned lo, unsigned hi, unsigned sh) { if (sh > 32) sh = 32; unsigned long long v = ((unsigned long long)hi << 32) | lo; return sh == 32 ? lo : (unsigned)((v << sh) >> 32); }
+static inline unsigned __funnelshift_rc(unsigned lo, unsigned hi, unsigned sh) { if (sh > 32) sh = 32; unsigned long long v = ((unsigned long long)hi << 32) | lo; return (unsigned)(v >> sh); }
 static inline int __double2hiint(double x) { long long v; memcpy(&v, &x, 8); return (int)(v >> 32); }
 static inline int __double2loint(double x) { long long v; memcpy(&v, &x, 8); return (int)(v & 0xffffffffLL); }
 static inline double __hiloint2double(int hi, int lo) { long long v = ((long long)hi << 32) | (unsigned)lo; double x; memcpy(&x, &v, 8); return x; }
