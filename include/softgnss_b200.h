@@ -137,6 +137,26 @@ int sgx_synth_generate(int8_t* out, int64_t rec_stride, int64_t n_samples, int64
  * over {2,3,5,7,11,31}.  The counterpart of np.fft.fft / n*np.fft.ifft at acquisition.py:95-126,182. */
 int sgx_fft_c2c(const float* in, float* out, int32_t n, int32_t batch, int32_t inverse, void* cuda_stream);
 
+#define SGX_NAV_BITS 1501
+
+/* Replaces NavigationResult.findPreambles (postNavigation.py:524-631) and the 20 ms bit summation of
+ * postNavigate (postNavigation.py:125-134) for n_channels tracked channels (the downstream consumer of
+ * the tracking result).
+ *   i_p             double [n_channels][stride] prompt in-phase series (host or device; e.g. field 3 of
+ *                   sgx_track's output with stride = SGX_TRACK_FIELDS * ms), ms values used per row
+ *   first_subframe  int32 [n_channels] (host or device): ms index of the first preamble that has a
+ *                   preamble-like pattern 6000 ms later and whose TLM and HOW words pass the parity
+ *                   check; 0 when there is none (the reference's convention)
+ *   nav_bits        optional uint8 [n_channels][SGX_NAV_BITS]: hard bits 0/1 of
+ *                   I_P[first-20 : first+30000] summed over 20 ms (bit 0 = last bit of the previous
+ *                   subframe), what the caller hands to ephemeris()
+ *   nav_bits_valid  optional int32 [n_channels]: 1 when that window lies inside the record
+ * Candidates nearer than 40 ms to the start of the record are passed over (the reference reads
+ * I_P[k-40:...] with a negative start there and raises). */
+int sgx_find_preambles(const double* i_p, int64_t stride, int32_t n_channels, int32_t ms,
+                       int32_t* first_subframe, uint8_t* nav_bits, int32_t* nav_bits_valid,
+                       void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

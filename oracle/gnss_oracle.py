@@ -284,3 +284,85 @@ def track(data, channels, s, ms=None):
             return None
         recs.append((int(channels["PRN"][ch]), channels["status"][ch], series))
     return recs
+
+
+# ---------------------------------------------------------------------------------------------
+# preamble search / bit synchronisation (postNavigation.py:524-631)
+# and the 20 ms bit summation of the caller (postNavigation.py:125-134).
+# ---------------------------------------------------------------------------------------------
+PREAMBLE_BITS = np.array([1, -1, -1, -1, 1, -1, 1, 1])                     # postNavigation.py:554
+
+
+def nav_party_chk(ndat):
+    """postNavigation.py:441-521 on a copy of 32 values of +-1: D29*, D30*, d1..d24, D25..D30.
+    Returns -D30* (+1 / -1) when the six parity equations hold, else 0."""
+    d = np.array(ndat, dtype=np.float64)
+    if d[1] != 1:                                                         # :469
+        d[2:26] *= -1
+    taps = ((0, 2, 3, 4, 6, 7, 11, 12, 13, 14, 15, 18, 19, 21, 24),       # :480-504, indices into ndat
+            (1, 3, 4, 5, 7, 8, 12, 13, 14, 15, 16, 19, 20, 22, 25),
+            (0, 2, 4, 5, 6, 8, 9, 13, 14, 15, 16, 17, 20, 21, 23),
+            (1, 3, 5, 6, 7, 9, 10, 14, 15, 16, 17, 18, 21, 22, 24),
+            (1, 2, 4, 6, 7, 8, 10, 11, 15, 16, 17, 18, 19, 22, 23, 25),
+            (0, 4, 6, 7, 9, 10, 11, 12, 14, 16, 20, 23, 24, 25))
+    parity = np.array([np.prod(d[list(t)]) for t in taps])
+    if (parity == d[26:]).sum() == 6:                                     # :507
+        return -1 * d[1]
+    return 0
+
+
+def sum20(i_p, start, n_bits):
+    """``I_P[start:start+20*n_bits].reshape(20, -1, order='F').sum(0)`` (postNavigation.py:596-598,
+    :127-129) -- numpy's own reduction, so the rounding order is the reference's by construction."""
+    seg = np.array(i_p[start:start + 20 * n_bits], dtype=np.float64)
+    return seg.reshape(20, -1, order="F").sum(0)
+
+
+def preamble_correlation(i_p):
+    """Lags 0..M-1 of ``np.correlate(bits, zero-padded preamble_ms, 'full')`` (postNavigation.py:571-584).
+    The reference evaluates the full M x M product; the 160 non-zero taps give the same integers."""
+    bits = np.where(np.asarray(i_p, dtype=np.float64) > 0, 1, -1).astype(np.int32)   # :567-569 (NaN, 0 -> -1)
+    pat = np.kron(PREAMBLE_BITS, np.ones(20, dtype=np.int32)).astype(np.int32)       # :558
+    m = bits.size
+    padded = np.concatenate([bits, np.zeros(pat.size, dtype=np.int32)])
+    win = np.lib.stride_tricks.sliding_window_view(padded, pat.size)[:m]
+    return win @ pat
+
+
+def find_preambles(i_p_list, skip_unreadable=True):
+    """postNavigation.py:524-631 for the tracked channels (status != '-') in result order.
+
+    Returns (firstSubFrame int array, activeChnList).  ``skip_unreadable``: a candidate nearer than
+    40 ms to the start of the record makes the reference read ``I_P[negative:positive]`` (an empty
+    slice) and crash in ``navPartyChk``; with the flag such candidates are passed over (the only
+    deviation, analogous to ``acquire(clamp_window=True)``)."""
+    n_ch = len(i_p_list)
+    first = np.zeros(n_ch, dtype=int)
+    for ch in range(n_ch):
+        i_p = np.asarray(i_p_list[ch], dtype=np.float64)
+        corr = preamble_correlation(i_p)
+        index = (np.abs(corr) > 153).nonzero()[0]                         # :584 (searchStartOffset = 0)
+        cand = set(index.tolist())
+        for k in index:
+            if (k + 6000) not in cand:                                    # :593-595
+                continue
+            if k < 40:
+                if skip_unreadable:
+                    continue
+                raise IndexError("reference reads I_P[%d:%d]" % (k - 40, k + 1200))
+            if k + 1200 > i_p.size:                                       # unreachable: k + 6000 is a candidate
+                continue
+            s = sum20(i_p, k - 40, 62)                                    # :594-598
+            bits = np.where(s > 0, 1, -1)                                 # :600-602
+            if nav_party_chk(bits[:32]) != 0 and nav_party_chk(bits[30:62]) != 0:   # :604
+                first[ch] = k
+                break
+    active = np.array([ch for ch in range(n_ch) if first[ch] != 0], dtype=int)      # :612-618
+    return first, active
+
+
+def nav_bits(i_p, sub_frame_start):
+    """postNavigation.py:125-134: 1501 hard bits (0/1) of the five subframes that start at
+    ``sub_frame_start``, preceded by the last bit of the subframe before."""
+    s = sum20(i_p, sub_frame_start - 20, 1501)
+    return (s > 0).astype(np.uint8)

@@ -19,7 +19,8 @@ TRACK_FIELDS = ("absoluteSample", "codeFreq", "carrFreq", "I_P", "I_E", "I_L", "
 SGX_ERR_SHORT = -3
 
 EXPORTS = ("sgx_abi_version", "sgx_last_error", "sgx_device_count", "sgx_set_device",
-           "sgx_kernel_launch_count", "sgx_acquire", "sgx_track", "sgx_synth_generate", "sgx_fft_c2c")
+           "sgx_kernel_launch_count", "sgx_acquire", "sgx_track", "sgx_synth_generate", "sgx_fft_c2c",
+           "sgx_find_preambles")
 
 
 class NativeError(RuntimeError):
@@ -111,6 +112,20 @@ class Lib(object):
         self.check(self.dll.sgx_fft_c2c(_ptr(x), _ptr(out), x.shape[1], x.shape[0], int(bool(inverse)),
                                         ctypes.c_void_p(stream)))
         return out
+
+    # ------------------------------------------------------------------ bit synchronisation
+    def find_preambles(self, i_p, stride, n_channels, ms, want_bits=True, stream=0):
+        """i_p: float64 [n_channels][stride] (numpy or CUDA tensor).  Returns (first int32[n], bits uint8[n,1501]
+        or None, valid int32[n] or None) as numpy arrays."""
+        self.require_device()
+        first = np.zeros(n_channels, dtype=np.int32)
+        bits = np.zeros((n_channels, 1501), dtype=np.uint8) if want_bits else None
+        valid = np.zeros(n_channels, dtype=np.int32) if want_bits else None
+        self.dll.sgx_find_preambles.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
+                                                ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        self.check(self.dll.sgx_find_preambles(_ptr(i_p), int(stride), int(n_channels), int(ms), _ptr(first),
+                                               _ptr(bits), _ptr(valid), ctypes.c_void_p(stream)))
+        return first, bits, valid
 
     # ------------------------------------------------------------------ synthetic recordings
     def synth(self, out, rec_stride, n_samples, start, specs, bits, lut, ca_chips, stream=0):

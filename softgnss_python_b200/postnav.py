@@ -1,0 +1,77 @@
+"""Preamble search and navigation-bit extraction on the B200 -- the first stage of the reference's
+downstream consumer (``postNavigation.py``), SURVEY.md section 8(f) row 3.
+
+Mirrors, with the reference's names and conventions:
+
+* ``findPreambles(trackResults, settings)`` -> ``(firstSubFrame, activeChnList)``
+  (``NavigationResult.findPreambles``, postNavigation.py:524-631);
+* ``navBitsBin(trackResults, firstSubFrame, channelNr)`` -> list of ``'0'``/``'1'`` strings
+  (postNavigation.py:125-139), ready for ``ephemeris.ephemeris(bits[1:], bits[0])``.
+
+``find_preambles_batch`` is the batched entry point over a float64 ``[channels, ms]`` array or CUDA tensor
+(e.g. field 3 of ``track_batch``'s device-resident output).  There is no CPU implementation here: the
+work is done by ``sgx_find_preambles`` (csrc/sgx_bitsync.cu) and the call fails without a CUDA device.
+"""
+import numpy as np
+
+from . import _native
+
+NAV_BITS = 1501
+
+
+def find_preambles_batch(i_p, ms=None, stride=None, want_bits=True, stream=0):
+    """``i_p``: float64 ``[n, ms]`` numpy array or CUDA tensor (rows ``stride`` elements apart).
+    Returns ``(first int32[n], bits uint8[n, 1501] | None, valid int32[n] | None)``."""
+    if isinstance(i_p, np.ndarray):
+        i_p = np.ascontiguousarray(i_p, dtype=np.float64)
+        n = i_p.shape[0]
+        ms = i_p.shape[1] if ms is None else int(ms)
+        stride = i_p.shape[1] if stride is None else int(stride)
+    else:                                   # torch tensor
+        import torch
+        assert i_p.dtype == torch.float64 and i_p.stride(-1) == 1
+        n = i_p.shape[0]
+        ms = i_p.shape[1] if ms is None else int(ms)
+        stride = i_p.stride(0) if stride is None else int(stride)
+    return _native.lib().find_preambles(i_p, stride, n, ms, want_bits=want_bits, stream=stream)
+
+
+def _tracked_ip(trackResults):
+    active = (trackResults.status != '-').nonzero()[0] if trackResults.status.dtype.kind != 'S' \
+        else (trackResults.status != b'-').nonzero()[0]
+    # (the reference indexes trackResults with range(len(activeChnList)), postNavigation.py:563)
+    rows = [np.asarray(trackResults[c].I_P, dtype=np.float64) for c in range(len(active))]
+    return active, (np.stack(rows) if rows else np.zeros((0, 1)))
+
+
+def findPreambles(trackResults, settings, return_bits=False):
+    """postNavigation.py:524-631.  ``firstSubFrame`` has ``settings.numberOfChannels`` entries (0 = none);
+    ``activeChnList`` lists the channels with a verified preamble."""
+    assert isinstance(trackResults, np.recarray)
+    firstSubFrame = np.zeros(settings.numberOfChannels, dtype=int)
+    activeChnList, i_p = _tracked_ip(trackResults)
+    bits = valid = None
+    if len(activeChnList):
+        first, bits, valid = find_preambles_batch(i_p)
+        firstSubFrame[:len(first)] = first
+    for channelNr in range(len(activeChnList)):
+        if firstSubFrame[channelNr] == 0:
+            activeChnList = np.setdiff1d(activeChnList, channelNr)
+            print('Could not find valid preambles in channel %2d !' % channelNr)
+    if return_bits:
+        return firstSubFrame, activeChnList, bits, valid
+    return firstSubFrame, activeChnList
+
+
+def navBitsBin(bits_row):
+    """The ``navBitsBin`` list of postNavigation.py:134-137 from one row of the device's hard bits."""
+    return [str(int(b)) for b in bits_row]
+
+
+def install(navigation_result_cls):
+    """Bind the B200 preamble search into the reference's own class:
+    ``NavigationResult.findPreambles`` keeps its signature and return value."""
+    def _find(self):
+        return findPreambles(self._results, self._settings)
+    navigation_result_cls.findPreambles = _find
+    return navigation_result_cls

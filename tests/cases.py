@@ -55,3 +55,71 @@ def case_settings(case):
     s = Settings(**case.get("settings", {}))
     s.msToProcess = float(case["ms"])
     return s
+
+
+# ---------------------------------------------------------------------------------------------
+# Bit-sync cases: prompt in-phase series I_P built directly from an
+# LNAV bit stream with integer-only noise (exactly reproducible from the seed on any numpy).
+# ---------------------------------------------------------------------------------------------
+BITSYNC_MS = 37000
+
+
+def _hash_noise(seed, n):
+    """Irwin-Hall noise as in softgnss_python_b200.synth: sum of the 8 bytes of splitmix64, mean removed."""
+    from softgnss_python_b200 import synth
+    i = np.arange(n, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        h = synth._splitmix64(np.uint64(seed) + i * np.uint64(synth.GOLDEN))
+    return h.view(np.uint8).reshape(-1, 8).sum(axis=1).astype(np.int64) - 1020     # sigma 209
+
+
+def _lnav_ms(seed, n_subframes=9, first_sf_id=1):
+    """+-1 per millisecond of `n_subframes` consecutive valid LNAV subframes."""
+    from softgnss_python_b200 import navsynth
+    rng = np.random.default_rng(seed)
+    e = dict(sqrtA=5153.6, e=0.004 + 0.001 * (seed % 3), i_0=np.radians(55.0), omega_0=0.3 * (seed % 7) - 1.0,
+             omega=-1.0, M_0=2.0, omegaDot=-8.0e-9, iDot=0.0, deltan=4.5e-9, t_oe=388800.0, weekNumber=2100,
+             IODE=int(rng.integers(1, 255)))
+    bits01 = navsynth.encode_stream(navsynth.quantize_ephemeris(e), first_sf_id, 388800 - 6, n_subframes)
+    return np.repeat(bits01.astype(np.int64) * 2 - 1, 20), bits01
+
+
+#  name: (first subframe boundary in ms, amplitude, noise scale, polarity, kind)
+BITSYNC_CHANNELS = [
+    dict(name="clean", boundary=3655, amp=4000, noise=6, pol=1),
+    dict(name="inverted", boundary=977, amp=4000, noise=6, pol=-1),
+    dict(name="random", boundary=0, amp=4000, noise=6, pol=1, random_bits=True),
+    dict(name="noisy", boundary=2222, amp=430, noise=1, pol=1),             # ~2 % of the ms have the wrong sign
+    dict(name="tlm_parity_broken", boundary=1500, amp=4000, noise=6, pol=1, flip_bit=12),   # first valid = +6000
+    dict(name="zeros", boundary=5999, amp=3000, noise=1, pol=-1, integer_ties=True),         # exact zeros -> -1
+    dict(name="late", boundary=41, amp=4000, noise=6, pol=1),
+    dict(name="weak", boundary=4321, amp=120, noise=1, pol=1),              # sign errors ~28 %: nothing found
+]
+BITSYNC_EARLY = dict(name="early", boundary=20, amp=4000, noise=6, pol=1)   # the reference crashes on this one
+
+
+def build_bitsync_channel(ch, seed):
+    ms, bits01 = _lnav_ms(seed)
+    if ch.get("random_bits"):
+        rng_bits = (_hash_noise(seed + 99, len(bits01)) & 1) * 2 - 1
+        ms = np.repeat(rng_bits, 20)
+    if "flip_bit" in ch:                       # corrupt one data bit of the first complete subframe's TLM word
+        b = 300 + ch["flip_bit"]
+        ms = ms.copy()
+        ms[20 * b:20 * b + 20] *= -1
+    w0 = 6000 - ch["boundary"]                 # subframe 2 of the stream starts at ms `boundary` of the window
+    sig = ms[w0:w0 + BITSYNC_MS] * ch["amp"] * ch["pol"]
+    noise = _hash_noise(seed, BITSYNC_MS) * ch["noise"]
+    ip = (sig + noise).astype(np.float64)
+    if ch.get("integer_ties"):
+        ip[::97] = 0.0                          # I_P == 0 counts as a -1 (postNavigation.py:569)
+        b0 = ch["boundary"] + 20 * 70           # one data bit whose 20 ms sum is exactly 0 -> bit 0 (:131)
+        ip[b0:b0 + 20] = np.tile([500.0, -500.0], 10)
+    else:
+        ip += 0.25                              # keep the 20 ms sums away from exact zero
+    return ip
+
+
+def build_bitsync_case(channels=None, seed0=500):
+    channels = BITSYNC_CHANNELS if channels is None else channels
+    return [build_bitsync_channel(ch, seed0 + i) for i, ch in enumerate(channels)]
