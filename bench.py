@@ -13,6 +13,7 @@ Primary line  : tracking channel-ms/s on BASELINE.json config 4 ("batched tracki
                 recordings are copied host->device and the 13 result series device->host inside the
                 timed region.
 `secondary`   : acquisition search cells/s (config 1 settings, a batch of 11 ms recordings per GPU).
+`tertiary`    : preamble search / nav-bit summation on the tracking result, channels/s.
 `roofline`    : tracking kernel, algorithmic bytes (38192 B in + 104 B out per channel-ms,
                 SURVEY.md section 8(d)) / CUDA-event duration vs the measured HBM copy bandwidth.
 `cpu_baseline`: the numpy oracle (a restatement of the reference's loops, oracle/gnss_oracle.py) timed
@@ -288,6 +289,50 @@ def run_gpu(args, rank, world):
                             "frac": cells * FLOP_PER_CELL / (a_ms / 1e3) / 1e12 / 74.5,
                             "note": "reference-formulation FLOPs (330/cell); peak = nominal 148 SM x 128 x 2 x 1.965 GHz"}}
 
+    # ---- tertiary: preamble search / bit summation on the device-resident tracking result (8(f) row 3) ----
+    bsync = None
+    if not args.no_acq and ms >= 160:
+        from softgnss_python_b200 import postnav
+        ipv = out.view(recs * CHANNELS, 13 * ms)[:, 3 * ms:4 * ms]      # I_P rows, row stride 13 * ms
+        for _ in range(args.warmup):
+            postnav.find_preambles_batch(ipv, stream=stream)
+        barrier()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        bl0 = L.launches()
+        b0.record()
+        for _ in range(args.steps):
+            first, nbits, nvalid = postnav.find_preambles_batch(ipv, stream=stream)
+        b1.record()
+        barrier()
+        tb = torch.tensor([b0.elapsed_time(b1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        b_ms = float(tb.item()) / args.steps
+        nch = recs * CHANNELS
+        bsync = {"metric": "preamble search channels/s", "value": world * nch / (b_ms / 1e3), "unit": "channels/s",
+                 "ms_per_step": b_ms, "gpu_launches": int(L.launches() - bl0),
+                 "config": {"workload": "sign bits + 160-tap preamble correlation at %d lags + parity verification + "
+                                        "1501 nav bits for %d channels per GPU (I_P of the tracking step above, "
+                                        "device resident; results copied to the host inside the timed region)" % (ms, nch),
+                            "channels_with_preamble": int((first > 0).sum())},
+                 "roofline": {"bound": "hbm", "achieved": nch * ms * 8 / (b_ms / 1e3) / 1e9, "peak": peaks()[0],
+                              "unit": "GB/s", "frac": nch * ms * 8 / (b_ms / 1e3) / 1e9 / peaks()[0],
+                              "note": "algorithmic bytes = 8 B per ms per channel (I_P read once)"}}
+        if rank == 0 and not args.no_cpu:
+            from oracle import gnss_oracle as orc
+            hip = [x.copy() for x in ipv[:CHANNELS].cpu().numpy()]
+            t0 = time.perf_counter()
+            of, _ = orc.find_preambles(hip)
+            for c in range(CHANNELS):
+                if of[c] and of[c] + 30000 <= ms:
+                    orc.nav_bits(hip[c], int(of[c]))
+            dt = time.perf_counter() - t0
+            bsync["cpu_baseline"] = {"value": CHANNELS / dt, "unit": "channels/s", "cores": 1, "kind": "port",
+                                     "sample": "%d channels x %d ms, oracle/gnss_oracle.py find_preambles (160-tap sliding "
+                                               "window; the reference's own M x M np.correlate takes ~0.24 s per channel)"
+                                               % (CHANNELS, ms)}
+            assert np.array_equal(of, first[:CHANNELS]), "bit sync differs from the oracle"
+
     ck = clocks.stop(c0, c1) if clocks else None
     if world > 1:
         counts = [None] * world
@@ -320,6 +365,7 @@ def run_gpu(args, rank, world):
                      "algorithmic_bytes_per_channel_ms": BYTES_PER_CHANNEL_MS, "peak_source": how},
         "clocks": ck,
         "secondary": acq,
+        "tertiary": bsync,
     }
     if not args.no_cpu:
         line["cpu_baseline"] = cpu_track_baseline(TRACK_CPU_MS, 1)

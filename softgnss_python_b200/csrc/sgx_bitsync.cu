@@ -101,12 +101,21 @@ __global__ void __launch_bounds__(BS_THREADS) bitsync_kernel(BitsyncArgs a) {
   if (tid == 0) best = 0x7fffffff;
   for (int w = a.n_words + tid; w < a.n_words + 8; w += BS_THREADS) sgn[w] = 0u;
 
-  // 1. sign bits
-  for (int w = warp; w < a.n_words; w += NWARPS) {
-    const int i = 32 * w + lane;
-    const bool pos = i < ms && ip[i] > 0.0;
-    const unsigned m = __ballot_sync(0xffffffffu, pos);
-    if (lane == 0) sgn[w] = m;
+  // 1. sign bits: eight independent 256-byte row segments in flight per warp before the ballots (a single load
+  //    per trip left the CTA waiting one DRAM latency per 32 samples)
+  constexpr int UNR = 8;
+  for (int w0 = warp * UNR; w0 < a.n_words; w0 += NWARPS * UNR) {
+    double v[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int i = 32 * (w0 + u) + lane;
+      v[u] = i < ms ? ip[i] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const unsigned m = __ballot_sync(0xffffffffu, v[u] > 0.0);
+      if (lane == 0 && w0 + u < a.n_words) sgn[w0 + u] = m;
+    }
   }
   __syncthreads();
 
@@ -119,21 +128,33 @@ __global__ void __launch_bounds__(BS_THREADS) bitsync_kernel(BitsyncArgs a) {
     unsigned x[7];
 #pragma unroll
     for (int q = 0; q < 7; ++q) x[q] = sgn[w + q];
-    for (int b = 0; b < 32; ++b) {
-      const int k = 32 * w + b;
-      if (k >= ms) break;
-      const int n = min(PRE_LEN, ms - k);
-      int agree = 0;
+    if (32 * w + 31 + PRE_LEN <= ms) {
+      // all 160 taps exist for the 32 lags of this word (every word but the last five of a record)
+#pragma unroll 4
+      for (int b = 0; b < 32; ++b) {
+        int differ = 0;
 #pragma unroll
-      for (int q = 0; q < 5; ++q) {
-        unsigned s = __funnelshift_r(x[q], x[q + 1], b);
-        unsigned eq = ~(s ^ pat[q]);
-        const int keep = n - 32 * q;                         // taps of this word that exist
-        if (keep < 32) eq &= keep <= 0 ? 0u : (0xFFFFFFFFu >> (32 - keep));
-        agree += __popc(eq);
+        for (int q = 0; q < 5; ++q) differ += __popc(__funnelshift_r(x[q], x[q + 1], b) ^ pat[q]);
+        const int c = PRE_LEN - 2 * differ;
+        if (c > PRE_THRESHOLD || -c > PRE_THRESHOLD) out |= 1u << b;
       }
-      const int c = 2 * agree - n;
-      if (c > PRE_THRESHOLD || -c > PRE_THRESHOLD) out |= 1u << b;
+    } else {
+      for (int b = 0; b < 32; ++b) {
+        const int k = 32 * w + b;
+        if (k >= ms) break;
+        const int n = min(PRE_LEN, ms - k);
+        int agree = 0;
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+          unsigned s = __funnelshift_r(x[q], x[q + 1], b);
+          unsigned eq = ~(s ^ pat[q]);
+          const int keep = n - 32 * q;                         // taps of this word that exist
+          if (keep < 32) eq &= keep <= 0 ? 0u : (0xFFFFFFFFu >> (32 - keep));
+          agree += __popc(eq);
+        }
+        const int c = 2 * agree - n;
+        if (c > PRE_THRESHOLD || -c > PRE_THRESHOLD) out |= 1u << b;
+      }
     }
     cand[w] = out;
   }
