@@ -45,6 +45,18 @@ FLOP_PER_CELL = 330.0                          # reference formulation, SURVEY.m
 TRACK_CPU_MS = 1000                            # bounded CPU sample (code periods per channel)
 
 
+_RESULT_FD = None
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -369,7 +381,7 @@ def run_gpu(args, rank, world):
     }
     if not args.no_cpu:
         line["cpu_baseline"] = cpu_track_baseline(TRACK_CPU_MS, 1)
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------ CPU arms
@@ -438,7 +450,7 @@ def run_reference(args, rank):
                                    "runs a bounded sample of it" % (REC_PER_GPU, CHANNELS, MS)},
             "cpu_baseline": base,
             "e2e": {"value": v, "unit": "channel-ms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -458,6 +470,12 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
+    # stdout carries exactly one JSON line: everything else that libraries write to fd 1 (NCCL prints its
+    # version banner there) goes to stderr
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank)
         return
