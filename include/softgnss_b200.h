@@ -157,6 +157,22 @@ int sgx_find_preambles(const double* i_p, int64_t stride, int32_t n_channels, in
                        int32_t* first_subframe, uint8_t* nav_bits, int32_t* nav_bits_valid,
                        void* cuda_stream);
 
+/* Replaces NavigationResult.calculatePseudoranges (postNavigation.py:27-72), batched over recordings and
+ * measurement epochs (first half; satellite positions and the least-squares
+ * fix stay with the reference's host code).
+ *   track_out     double [n_recordings][n_channels][SGX_TRACK_FIELDS][ms] as written by sgx_track (host or
+ *                 device); only field 0 (absoluteSample) is read
+ *   ms_index      int32 [n_recordings][n_epochs][n_channels]: msOfTheSignal per channel
+ *   active        uint8 [n_recordings][n_epochs][n_channels]: 1 = channel is in channelList (others get +inf
+ *                 travel time, i.e. an infinite pseudorange, as in the reference)
+ *   pseudoranges  double [n_recordings][n_epochs][n_channels], metres:
+ *                 (absoluteSample[ms_index]/samples_per_code - floor(min over the list) + start_offset) * c / 1000
+ * n_channels <= 32.  Bit-identical to the reference (same float64 operations in the same order). */
+int sgx_pseudoranges(const double* track_out, int32_t n_recordings, int32_t n_channels, int32_t ms,
+                     const int32_t* ms_index, const uint8_t* active, int32_t n_epochs,
+                     double samples_per_code, double start_offset, double c, double* pseudoranges,
+                     void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -366,3 +366,18 @@ def nav_bits(i_p, sub_frame_start):
     ``sub_frame_start``, preceded by the last bit of the subframe before."""
     s = sum20(i_p, sub_frame_start - 20, 1501)
     return (s > 0).astype(np.uint8)
+
+
+# ---------------------------------------------------------------------------------------------
+# SURVEY.md section 8(f) row 4, first half: relative pseudoranges (postNavigation.py:27-72)
+# ---------------------------------------------------------------------------------------------
+def calculate_pseudoranges(abs_sample, ms_of_the_signal, channel_list, n_channels, samples_per_code,
+                           start_offset=68.802, c=299792458.0):
+    """postNavigation.py:52-72.  ``abs_sample[ch]`` is the absoluteSample series of channel ch."""
+    travel = np.inf * np.ones(n_channels)                                  # :52
+    for ch in channel_list:                                                 # :58-61
+        travel[ch] = abs_sample[ch][int(ms_of_the_signal[ch])] / samples_per_code
+    with np.errstate(invalid="ignore"):
+        minimum = np.floor(travel.min())                                    # :64
+        travel = travel - minimum + start_offset                            # :66
+        return travel * c / 1000                                            # :71

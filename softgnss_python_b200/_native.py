@@ -20,7 +20,7 @@ SGX_ERR_SHORT = -3
 
 EXPORTS = ("sgx_abi_version", "sgx_last_error", "sgx_device_count", "sgx_set_device",
            "sgx_kernel_launch_count", "sgx_acquire", "sgx_track", "sgx_synth_generate", "sgx_fft_c2c",
-           "sgx_find_preambles")
+           "sgx_find_preambles", "sgx_pseudoranges")
 
 
 class NativeError(RuntimeError):
@@ -126,6 +126,22 @@ class Lib(object):
         self.check(self.dll.sgx_find_preambles(_ptr(i_p), int(stride), int(n_channels), int(ms), _ptr(first),
                                                _ptr(bits), _ptr(valid), ctypes.c_void_p(stream)))
         return first, bits, valid
+
+    def pseudoranges(self, track_out, n_rec, n_ch, ms, ms_index, active, samples_per_code, start_offset, c, stream=0):
+        """track_out: float64 [n_rec][n_ch][13][ms] (numpy or CUDA tensor); ms_index int32 / active uint8
+        [n_rec][n_epochs][n_ch].  Returns float64 [n_rec][n_epochs][n_ch]."""
+        self.require_device()
+        ms_index = np.ascontiguousarray(ms_index, dtype=np.int32).reshape(n_rec, -1, n_ch)
+        active = np.ascontiguousarray(active, dtype=np.uint8).reshape(n_rec, -1, n_ch)
+        n_ep = ms_index.shape[1]
+        out = np.empty((n_rec, n_ep, n_ch), dtype=np.float64)
+        self.dll.sgx_pseudoranges.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                              ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_double,
+                                              ctypes.c_double, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]
+        self.check(self.dll.sgx_pseudoranges(_ptr(track_out), n_rec, n_ch, int(ms), _ptr(ms_index), _ptr(active), n_ep,
+                                             float(samples_per_code), float(start_offset), float(c), _ptr(out),
+                                             ctypes.c_void_p(stream)))
+        return out
 
     # ------------------------------------------------------------------ synthetic recordings
     def synth(self, out, rec_stride, n_samples, start, specs, bits, lut, ca_chips, stream=0):

@@ -257,3 +257,85 @@ extern "C" int sgx_find_preambles(const double* i_p, int64_t stride, int32_t n_c
   if (!first_dev || (nav_bits && !bits_dev) || (nav_bits_valid && !valid_dev)) SGX_CUDA(cudaStreamSynchronize(s));
   return SGX_OK;
 }
+
+// ---- relative pseudoranges (postNavigation.py:27-72), batched over recordings x measurement epochs ---------
+namespace sgx {
+struct PseudoArgs {
+  const double* trk;      // [n_rec][n_ch][SGX_TRACK_FIELDS][ms]; field 0 = absoluteSample
+  const int* ms_index;    // [n_rec][n_epochs][n_ch]
+  const unsigned char* active;   // [n_rec][n_epochs][n_ch]
+  double* pr;             // [n_rec][n_epochs][n_ch]
+  int n_rec, n_ch, n_epochs, ms;
+  double samples_per_code, start_offset, c;
+};
+
+// one warp per (recording, epoch); lane = channel (n_ch <= 32)
+__global__ void pseudorange_kernel(PseudoArgs a) {
+  const int unit = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (unit >= a.n_rec * a.n_epochs) return;
+  const int r = unit / a.n_epochs;
+  const long long o = (long long)unit * a.n_ch + lane;
+  double t = __longlong_as_double(0x7ff0000000000000LL);                    // +inf: not in the list (:52)
+  if (lane < a.n_ch && a.active[o]) {
+    const int i = a.ms_index[o];
+    if (i >= 0 && i < a.ms)
+      t = a.trk[(((long long)r * a.n_ch + lane) * SGX_TRACK_FIELDS) * a.ms + i] / a.samples_per_code;   // :60
+  }
+  double m = t;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, d));
+  if (lane < a.n_ch) a.pr[o] = ((t - floor(m)) + a.start_offset) * a.c / 1000.0;   // :64-71, same operation order
+}
+}  // namespace sgx
+
+extern "C" int sgx_pseudoranges(const double* track_out, int32_t n_recordings, int32_t n_channels, int32_t ms,
+                                const int32_t* ms_index, const uint8_t* active, int32_t n_epochs,
+                                double samples_per_code, double start_offset, double c, double* pseudoranges,
+                                void* cuda_stream) {
+  if (sgx_device_count() <= 0) return fail(SGX_ERR_NODEV, "sgx_pseudoranges", "no CUDA device");
+  if (!track_out || !ms_index || !active || !pseudoranges || n_channels < 1 || n_channels > 32 || ms <= 0 ||
+      n_recordings < 0 || n_epochs < 0)
+    return fail(SGX_ERR_ARG, "sgx_pseudoranges", "bad argument (1..32 channels)");
+  const long long units = (long long)n_recordings * n_epochs;
+  if (units == 0) return SGX_OK;
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  static DevBuf d_trk, d_idx, d_act, d_pr;
+  const size_t n = (size_t)units * n_channels;
+  PseudoArgs a;
+  a.trk = track_out;
+  if (!is_device_ptr(track_out)) {
+    const size_t bytes = sizeof(double) * (size_t)n_recordings * n_channels * SGX_TRACK_FIELDS * ms;
+    if (d_trk.reserve(bytes)) return fail(SGX_ERR_CUDA, "cudaMalloc", "tracking result");
+    SGX_CUDA(cudaMemcpyAsync(d_trk.p, track_out, bytes, cudaMemcpyHostToDevice, s));
+    a.trk = d_trk.as<double>();
+  }
+  a.ms_index = ms_index;
+  if (!is_device_ptr(ms_index)) {
+    if (d_idx.reserve(sizeof(int) * n)) return fail(SGX_ERR_CUDA, "cudaMalloc", "ms_index");
+    SGX_CUDA(cudaMemcpyAsync(d_idx.p, ms_index, sizeof(int) * n, cudaMemcpyHostToDevice, s));
+    a.ms_index = d_idx.as<int>();
+  }
+  a.active = active;
+  if (!is_device_ptr(active)) {
+    if (d_act.reserve(n)) return fail(SGX_ERR_CUDA, "cudaMalloc", "active");
+    SGX_CUDA(cudaMemcpyAsync(d_act.p, active, n, cudaMemcpyHostToDevice, s));
+    a.active = d_act.as<unsigned char>();
+  }
+  const bool out_dev = is_device_ptr(pseudoranges);
+  a.pr = pseudoranges;
+  if (!out_dev) {
+    if (d_pr.reserve(sizeof(double) * n)) return fail(SGX_ERR_CUDA, "cudaMalloc", "pseudoranges");
+    a.pr = d_pr.as<double>();
+  }
+  a.n_rec = n_recordings; a.n_ch = n_channels; a.n_epochs = n_epochs; a.ms = ms;
+  a.samples_per_code = samples_per_code; a.start_offset = start_offset; a.c = c;
+  const int threads = 256;
+  const long long blocks = (units * 32 + threads - 1) / threads;
+  SGX_COUNTED_LAUNCH(pseudorange_kernel, dim3((unsigned)blocks), dim3(threads), 0, s, a);
+  SGX_CUDA(cudaGetLastError());
+  if (!out_dev) {
+    SGX_CUDA(cudaMemcpyAsync(pseudoranges, a.pr, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+    SGX_CUDA(cudaStreamSynchronize(s));
+  }
+  return SGX_OK;
+}

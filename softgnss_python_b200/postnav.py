@@ -68,10 +68,36 @@ def navBitsBin(bits_row):
     return [str(int(b)) for b in bits_row]
 
 
+def calculatePseudoranges(trackResults, msOfTheSignal, channelList, settings):
+    """postNavigation.py:27-72 for one measurement epoch (function-style form of the reference method)."""
+    n_ch = settings.numberOfChannels
+    ms = len(trackResults[0].absoluteSample)
+    trk = np.zeros((1, n_ch, len(_native.TRACK_FIELDS), ms))
+    for c in range(min(n_ch, len(trackResults))):
+        trk[0, c, 0] = trackResults[c].absoluteSample
+    idx = np.zeros((1, 1, n_ch), dtype=np.int32)
+    act = np.zeros((1, 1, n_ch), dtype=np.uint8)
+    for c in channelList:
+        idx[0, 0, c] = int(msOfTheSignal[c])
+        act[0, 0, c] = 1
+    return pseudoranges_batch(trk, idx, act, settings)[0, 0]
+
+
+def pseudoranges_batch(track_out, ms_index, active, settings, stream=0):
+    """``track_out``: float64 ``[R, C, 13, ms]`` numpy array or CUDA tensor (``track_batch``'s output);
+    ``ms_index`` / ``active``: ``[R, E, C]``.  Returns metres, float64 ``[R, E, C]``."""
+    r, c, _, ms = track_out.shape
+    return _native.lib().pseudoranges(track_out, r, c, ms, ms_index, active, settings.samplesPerCode,
+                                      settings.startOffset, settings.c, stream=stream)
+
+
 def install(navigation_result_cls):
     """Bind the B200 preamble search into the reference's own class:
     ``NavigationResult.findPreambles`` keeps its signature and return value."""
     def _find(self):
         return findPreambles(self._results, self._settings)
+    def _pseudo(self, msOfTheSignal, channelList):
+        return calculatePseudoranges(self._results, msOfTheSignal, channelList, self._settings)
     navigation_result_cls.findPreambles = _find
+    navigation_result_cls.calculatePseudoranges = _pseudo
     return navigation_result_cls

@@ -123,3 +123,24 @@ def build_bitsync_channel(ch, seed):
 def build_bitsync_case(channels=None, seed0=500):
     channels = BITSYNC_CHANNELS if channels is None else channels
     return [build_bitsync_channel(ch, seed0 + i) for i, ch in enumerate(channels)]
+
+
+# ---------------------------------------------------------------------------------------------
+# Pseudorange cases (first half)
+# ---------------------------------------------------------------------------------------------
+def build_pseudo_case(n_ch=8, ms=2000, n_epochs=6, seed=77):
+    """absoluteSample-like series (integer-valued float64, one code period per ms with a slow drift),
+    msOfTheSignal per epoch/channel and channel lists of varying size (including an empty one)."""
+    noise = _hash_noise(seed, n_ch * ms).reshape(n_ch, ms)
+    start = 1000 + 4000 * np.arange(n_ch)[:, None] + (_hash_noise(seed + 1, n_ch)[:, None] % 977)
+    drift = np.cumsum(38192 + (noise % 3) - 1, axis=1)
+    abs_sample = (start + drift).astype(np.float64)
+    sub = 40 + (np.abs(_hash_noise(seed + 2, n_ch)) % 900)                     # "subFrameStart" per channel
+    ms_index = (sub[None, :] + 150 * np.arange(n_epochs)[:, None]).astype(np.int32)
+    active = np.ones((n_epochs, n_ch), dtype=np.uint8)
+    active[1, [2, 5]] = 0
+    active[2, :] = 0
+    active[2, [0, 3, 4, 7]] = 1
+    active[3, :] = 0                                                           # empty list: all inf - inf = nan
+    active[4, 1:] = 0                                                          # a single channel
+    return abs_sample, ms_index, active

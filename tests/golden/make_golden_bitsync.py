@@ -22,7 +22,7 @@ sys.path.insert(0, ROOT)
 
 from oracle import make_ref_shim                                  # noqa: E402
 from oracle.gnss_oracle import TRACK_FIELDS                      # noqa: E402
-from tests.cases import build_bitsync_case, BITSYNC_MS          # noqa: E402
+from tests.cases import build_bitsync_case, build_pseudo_case, BITSYNC_MS          # noqa: E402
 
 
 def main():
@@ -57,6 +57,31 @@ def main():
                         nav_bits=np.packbits(bits, axis=1), bits_valid=bits_valid,
                         input_sha1=hashlib.sha1(np.ascontiguousarray(np.stack(ips)).tobytes()).hexdigest())
     print("firstSubFrame", first, "active", active)
+
+    # ---- calculatePseudoranges (postNavigation.py:27-72) on synthetic absoluteSample series ----------------
+    abs_sample, ms_index, act = build_pseudo_case()
+    n_ch, n_ms = abs_sample.shape
+    s2 = ref["initialize"].Settings()
+    s2.numberOfChannels = n_ch
+    zero = np.zeros(n_ms)
+    rec = [(b'T',) + tuple(abs_sample[c] if f == "absoluteSample" else zero for f in TRACK_FIELDS) + (c + 1,)
+           for c in range(n_ch)]
+    res2 = np.rec.fromrecords(rec, dtype=dtype)
+
+    class T2(object):
+        results = res2
+        channels = None
+        settings = s2
+    nav2 = ref["postNavigation"].NavigationResult(T2())
+    pr = np.zeros(ms_index.shape)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for e in range(ms_index.shape[0]):
+            pr[e] = nav2.calculatePseudoranges(ms_index[e].astype(float), act[e].nonzero()[0])
+    np.savez_compressed(os.path.join(HERE, "pseudo.npz"), pseudoranges=pr,
+                        input_sha1=hashlib.sha1(np.ascontiguousarray(abs_sample).tobytes()).hexdigest())
+    print("pseudoranges epoch 0:", pr[0][:3], "epoch 3 (empty list):", pr[3][:2])
 
 
 if __name__ == "__main__":

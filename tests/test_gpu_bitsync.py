@@ -101,3 +101,35 @@ def test_bitsync_on_tracking_output_of_the_lnav_scenario():
     for ch in range(8):
         assert valid[ch] == 1
         assert np.array_equal(nb[ch], orc.nav_bits(ip[ch], int(of[ch])))
+
+
+def test_pseudoranges_bit_identical_to_reference():
+    import torch
+    from softgnss_python_b200 import postnav
+    from softgnss_python_b200.settings import Settings
+    from tests.cases import build_pseudo_case
+    abs_sample, ms_index, act = build_pseudo_case()
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "pseudo.npz"), allow_pickle=False)
+    n_ch, ms = abs_sample.shape
+    s = Settings(numberOfChannels=n_ch)
+    # batch of 3 "recordings": the case, the case shifted by whole code periods (same pseudoranges), a copy
+    trk = np.zeros((3, n_ch, 13, ms))
+    trk[0, :, 0] = abs_sample
+    trk[1, :, 0] = abs_sample + 5 * 38192
+    trk[2, :, 0] = abs_sample
+    idx = np.broadcast_to(ms_index, (3,) + ms_index.shape).copy()
+    a = np.broadcast_to(act, (3,) + act.shape).copy()
+    pr = postnav.pseudoranges_batch(trk, idx, a, s)
+    assert np.array_equal(pr[0], g["pseudoranges"], equal_nan=True)
+    assert np.array_equal(pr[2], pr[0], equal_nan=True)
+    assert np.allclose(pr[1], pr[0], rtol=0, atol=1e-6, equal_nan=True)
+    prd = postnav.pseudoranges_batch(torch.from_numpy(trk).cuda(), idx, a, s)          # device-resident input
+    assert np.array_equal(prd, pr, equal_nan=True)
+    # function-style mirror of the reference method, one epoch
+    dtype = [('status', 'U1')] + [(f, 'object') for f in orc.TRACK_FIELDS] + [('PRN', 'int64')]
+    zero = np.zeros(ms)
+    rec = [('T',) + tuple(abs_sample[c] if f == "absoluteSample" else zero for f in orc.TRACK_FIELDS) + (c + 1,)
+           for c in range(n_ch)]
+    res = np.rec.fromrecords(rec, dtype=dtype)
+    one = postnav.calculatePseudoranges(res, ms_index[1].astype(float), act[1].nonzero()[0], s)
+    assert np.array_equal(one, g["pseudoranges"][1])

@@ -61,3 +61,14 @@ def test_candidate_too_close_to_the_start():
     assert first[0] == 6020 and list(active) == [0]
     with pytest.raises(IndexError):
         orc.find_preambles([ip], skip_unreadable=False)
+
+
+def test_pseudoranges_match_reference():
+    from tests.cases import build_pseudo_case
+    abs_sample, ms_index, act = build_pseudo_case()
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "pseudo.npz"), allow_pickle=False)
+    assert hashlib.sha1(np.ascontiguousarray(abs_sample).tobytes()).hexdigest() == str(g["input_sha1"])
+    for e in range(ms_index.shape[0]):
+        got = orc.calculate_pseudoranges(abs_sample, ms_index[e], act[e].nonzero()[0], abs_sample.shape[0], 38192)
+        assert np.array_equal(got, g["pseudoranges"][e], equal_nan=True), e
+    assert np.isinf(g["pseudoranges"][1][2]) and np.isnan(g["pseudoranges"][3]).all()
