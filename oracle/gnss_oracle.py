@@ -381,3 +381,297 @@ def calculate_pseudoranges(abs_sample, ms_of_the_signal, channel_list, n_channel
         minimum = np.floor(travel.min())                                    # :64
         travel = travel - minimum + start_offset                            # :66
         return travel * c / 1000                                            # :71
+
+
+# ---------------------------------------------------------------------------------------------
+# SURVEY.md section 8(f) row 4, second half: satellite positions, least-squares fix and the
+# measurement-epoch loop of postNavigate (postNavigation.py:159-301, geoFunctions/__init__.py).
+# Scalar float64 arithmetic in the reference's own operation order (np.float64 scalars, numpy ufuncs).
+# ---------------------------------------------------------------------------------------------
+EPH_FIELDS = ("t_oc", "a_f2", "a_f1", "a_f0", "T_GD", "sqrtA", "t_oe", "deltan", "M_0", "e", "omega",
+              "C_uc", "C_us", "C_rc", "C_rs", "i_0", "iDot", "C_ic", "C_is", "omega_0", "omegaDot")
+
+
+def check_t(time):
+    """geoFunctions/__init__.py:745-771: week crossover."""
+    half_week = 302400.0
+    if time > half_week:
+        return time - 2 * half_week
+    if time < -half_week:
+        return time + 2 * half_week
+    return time
+
+
+def satpos(transmit_time, prn_list, eph):
+    """geoFunctions/__init__.py:779-885.  ``eph[prn-1]`` is a mapping with the EPH_FIELDS keys.
+    Returns (satPositions float64 [3, n], satClkCorr float64 [n])."""
+    n_sat = len(prn_list)
+    gps_pi = 3.14159265359                                                  # :798
+    omegae_dot = 7.2921151467e-05                                           # :803
+    gm = 3.986005e+14                                                       # :805
+    f_rel = -4.442807633e-10                                                # :808
+    clk = np.zeros(n_sat)
+    pos = np.zeros((3, n_sat))
+    for k in range(n_sat):
+        e = {key: np.float64(eph[int(prn_list[k]) - 1][key]) for key in EPH_FIELDS}
+        dt = check_t(transmit_time - e["t_oc"])                             # :823
+        clk[k] = (e["a_f2"] * dt + e["a_f1"]) * dt + e["a_f0"] - e["T_GD"]  # :825
+        time = transmit_time - clk[k]                                       # :827
+        a = e["sqrtA"] * e["sqrtA"]                                         # :831
+        tk = check_t(time - e["t_oe"])                                      # :833
+        n0 = np.sqrt(gm / a ** 3)                                           # :835
+        n = n0 + e["deltan"]
+        m = e["M_0"] + n * tk
+        m = np.remainder(m + 2 * gps_pi, 2 * gps_pi)                        # :841
+        ea = m
+        for _ in range(10):                                                 # :845-853
+            ea_old = ea
+            ea = m + e["e"] * np.sin(ea)
+            d_e = np.remainder(ea - ea_old, 2 * gps_pi)
+            if abs(d_e) < 1e-12:
+                break
+        ea = np.remainder(ea + 2 * gps_pi, 2 * gps_pi)                      # :855
+        dtr = f_rel * e["e"] * e["sqrtA"] * np.sin(ea)                      # :857
+        nu = np.arctan2(np.sqrt(1 - e["e"] ** 2) * np.sin(ea), np.cos(ea) - e["e"])   # :859
+        phi = nu + e["omega"]
+        phi = np.remainder(phi, 2 * gps_pi)                                 # :863
+        u = phi + e["C_uc"] * np.cos(2 * phi) + e["C_us"] * np.sin(2 * phi)            # :865
+        r = a * (1 - e["e"] * np.cos(ea)) + e["C_rc"] * np.cos(2 * phi) + e["C_rs"] * np.sin(2 * phi)
+        inc = e["i_0"] + e["iDot"] * tk + e["C_ic"] * np.cos(2 * phi) + e["C_is"] * np.sin(2 * phi)
+        om = e["omega_0"] + (e["omegaDot"] - omegae_dot) * tk - omegae_dot * e["t_oe"]   # :871
+        om = np.remainder(om + 2 * gps_pi, 2 * gps_pi)
+        pos[0, k] = np.cos(u) * r * np.cos(om) - np.sin(u) * r * np.cos(inc) * np.sin(om)   # :875
+        pos[1, k] = np.cos(u) * r * np.sin(om) + np.sin(u) * r * np.cos(inc) * np.cos(om)
+        pos[2, k] = np.sin(u) * r * np.sin(inc)
+        clk[k] = (e["a_f2"] * dt + e["a_f1"]) * dt + e["a_f0"] - e["T_GD"] + dtr        # :882
+    return pos, clk
+
+
+def e_r_corr(traveltime, x_sat):
+    """geoFunctions/__init__.py:491-521: rotate by the Earth's rotation during the flight."""
+    omegatau = 7.292115147e-05 * traveltime                                 # :508-511 (this constant, not satpos's)
+    r3 = np.array([[np.cos(omegatau), np.sin(omegatau), 0.0],
+                   [-np.sin(omegatau), np.cos(omegatau), 0.0],
+                   [0.0, 0.0, 1.0]])
+    return r3.dot(x_sat)
+
+
+def togeod(a, finv, x, y, z):
+    """geoFunctions/__init__.py:892-1000: geodetic latitude/longitude (degrees) and height."""
+    h = 0.0
+    tolsq = 1e-10
+    maxit = 10
+    rtd = 180 / np.pi
+    esq = 0.0 if finv < 1e-20 else (2 - 1 / finv) / finv
+    oneesq = 1 - esq
+    p = np.sqrt(x ** 2 + y ** 2)
+    dlambda = np.arctan2(y, x) * rtd if p > 1e-20 else 0.0
+    if dlambda < 0:
+        dlambda = dlambda + 360
+    r = np.sqrt(p ** 2 + z ** 2)
+    sinphi = z / r if r > 1e-20 else 0.0
+    dphi = np.arcsin(sinphi)
+    if r < 1e-20:
+        return dphi, dlambda, 0.0
+    h = r - a * (1 - sinphi * sinphi / finv)
+    for _ in range(maxit):
+        sinphi = np.sin(dphi)
+        cosphi = np.cos(dphi)
+        n_phi = a / np.sqrt(1 - esq * sinphi * sinphi)
+        d_p = p - (n_phi + h) * cosphi
+        d_z = z - (n_phi * oneesq + h) * sinphi
+        h = h + sinphi * d_z + cosphi * d_p
+        dphi = dphi + (cosphi * d_z - sinphi * d_p) / (n_phi + h)
+        if (d_p * d_p + d_z * d_z) < tolsq:
+            break
+    dphi *= rtd
+    return dphi, dlambda, h
+
+
+def topocent(x, dx):
+    """geoFunctions/__init__.py:1003-1063: azimuth, elevation (degrees) and length of dx seen from x."""
+    dtr = np.pi / 180
+    phi, lambda_, _ = togeod(6378137, 298.257223563, x[0], x[1], x[2])
+    cl = np.cos(lambda_ * dtr)
+    sl = np.sin(lambda_ * dtr)
+    cb = np.cos(phi * dtr)
+    sb = np.sin(phi * dtr)
+    f = np.array([[-sl, -sb * cl, cb * cl], [cl, -sb * sl, cb * sl], [0.0, cb, sb]])
+    local = f.T.dot(dx)
+    e, n, u = local[0], local[1], local[2]
+    hor_dis = np.sqrt(e ** 2 + n ** 2)
+    if hor_dis < 1e-20:
+        az, el = 0.0, 90.0
+    else:
+        az = np.arctan2(e, n) / dtr
+        el = np.arctan2(u, hor_dis) / dtr
+    if az < 0:
+        az = az + 360
+    d = np.sqrt(dx[0] ** 2 + dx[1] ** 2 + dx[2] ** 2)
+    return az, el, d
+
+
+def tropo(sinel, hsta, p, tkel, hum, hp, htkel, hhum):
+    """geoFunctions/__init__.py:1071-1169: Goad-Goodman tropospheric delay in metres."""
+    a_e = 6378.137
+    b0 = 7.839257e-05
+    tlapse = -6.5
+    tkhum = tkel + tlapse * (hhum - htkel)
+    atkel = 7.5 * (tkhum - 273.15) / (237.3 + tkhum - 273.15)
+    e0 = 0.0611 * hum * 10 ** atkel
+    tksea = tkel - tlapse * htkel
+    em = -978.77 / (2870400.0 * tlapse * 1e-05)
+    tkelh = tksea + tlapse * hhum
+    e0sea = e0 * (tksea / tkelh) ** (4 * em)
+    tkelp = tksea + tlapse * hp
+    psea = p * (tksea / tkelp) ** em
+    if sinel < 0:
+        sinel = 0
+    tropo_ = 0.0
+    done = False
+    refsea = 7.7624e-05 / tksea
+    htop = 1.1385e-05 / refsea
+    refsea = refsea * psea
+    ref = refsea * ((htop - hsta) / htop) ** 4
+    while 1:
+        rtop = (a_e + htop) ** 2 - (a_e + hsta) ** 2 * (1 - sinel ** 2)
+        if rtop < 0:
+            rtop = 0
+        rtop = np.sqrt(rtop) - (a_e + hsta) * sinel
+        a = -sinel / (htop - hsta)
+        b = -b0 * (1 - sinel ** 2) / (htop - hsta)
+        rn = np.zeros(8)
+        for i in range(8):
+            rn[i] = rtop ** (i + 2)
+        alpha = np.array([2 * a, 2 * a ** 2 + 4 * b / 3, a * (a ** 2 + 3 * b),
+                          a ** 4 / 5 + 2.4 * a ** 2 * b + 1.2 * b ** 2,
+                          2 * a * b * (a ** 2 + 3 * b) / 3,
+                          b ** 2 * (6 * a ** 2 + 4 * b) * 0.1428571, 0, 0])
+        if b ** 2 > 1e-35:
+            alpha[6] = a * b ** 3 / 2
+            alpha[7] = b ** 4 / 9
+        dr = rtop
+        dr = dr + alpha.dot(rn)
+        tropo_ += dr * ref * 1000
+        if done:
+            return tropo_
+        done = True
+        refsea = (0.3719 / tksea - 1.292e-05) / tksea
+        htop = 1.1385e-05 * (1255.0 / tksea + 0.05) / refsea
+        ref = refsea * e0sea * ((htop - hsta) / htop) ** 4
+
+
+def least_square_pos(satpos_, obs, c=299792458.0, use_trop_corr=True):
+    """geoFunctions/__init__.py:636-739.  Returns (pos[4], el[n], az[n], dop[5]).
+    Quirks kept: the design-matrix rows are divided by obs[i] (not by the geometric range, :706-709);
+    ``trop = 2`` in the first iteration (:683); DOP from the last iteration's A (:726)."""
+    dtr = np.pi / 180
+    pos = np.zeros(4)
+    x_all = satpos_.copy()
+    n = satpos_.shape[1]
+    a_mat = np.zeros((n, 4))
+    omc = np.zeros(n)
+    az = np.zeros(n)
+    el = np.zeros(n)
+    dop = np.zeros(5)
+    for it in range(7):                                                      # :659
+        for i in range(n):
+            if it == 0:
+                rot_x = x_all[:, i].copy()
+                trop = 2
+            else:
+                rho2 = (x_all[0, i] - pos[0]) ** 2 + (x_all[1, i] - pos[1]) ** 2 + (x_all[2, i] - pos[2]) ** 2
+                traveltime = np.sqrt(rho2) / c
+                rot_x = e_r_corr(traveltime, x_all[:, i])
+                az[i], el[i], _ = topocent(pos[0:3], rot_x - pos[0:3])
+                if use_trop_corr:
+                    trop = tropo(np.sin(el[i] * dtr), 0.0, 1013.0, 293.0, 50.0, 0.0, 0.0, 0.0)
+                else:
+                    trop = 0
+            omc[i] = obs[i] - np.linalg.norm(rot_x - pos[0:3]) - pos[3] - trop          # :704
+            a_mat[i, :] = np.array([-(rot_x[0] - pos[0]) / obs[i], -(rot_x[1] - pos[1]) / obs[i],
+                                    -(rot_x[2] - pos[2]) / obs[i], 1])
+        if np.linalg.matrix_rank(a_mat) != 4:                                # :712-715
+            return np.zeros(4), el, az, dop
+        x = np.linalg.lstsq(a_mat, omc, rcond=None)[0]                       # :717
+        pos = pos + x.flatten()
+    q = np.linalg.inv(a_mat.T.dot(a_mat))                                    # :726
+    dop[0] = np.sqrt(np.trace(q))
+    dop[1] = np.sqrt(q[0, 0] + q[1, 1] + q[2, 2])
+    dop[2] = np.sqrt(q[0, 0] + q[1, 1])
+    dop[3] = np.sqrt(q[2, 2])
+    dop[4] = np.sqrt(q[3, 3])
+    return pos, el, az, dop
+
+
+def cart2geo(x, y, z, i=4):
+    """geoFunctions/__init__.py:7-77 (ellipsoid 4 = WGS84): latitude, longitude (degrees), height."""
+    a = np.array([6378388.0, 6378160.0, 6378135.0, 6378137.0, 6378137.0])
+    f = np.array([1 / 297, 1 / 298.247, 1 / 298.26, 1 / 298.257222101, 1 / 298.257223563])
+    lambda_ = np.arctan2(y, x)
+    ex2 = (2 - f[i]) * f[i] / ((1 - f[i]) ** 2)
+    c = a[i] * np.sqrt(1 + ex2)
+    phi = np.arctan(z / (np.sqrt(x ** 2 + y ** 2) * (1 - (2 - f[i])) * f[i]))
+    h = 0.1
+    oldh = 0
+    iterations = 0
+    while abs(h - oldh) > 1e-12:
+        oldh = h
+        n = c / np.sqrt(1 + ex2 * np.cos(phi) ** 2)
+        phi = np.arctan(z / (np.sqrt(x ** 2 + y ** 2) * (1 - (2 - f[i]) * f[i] * n / (n + h))))
+        h = np.sqrt(x ** 2 + y ** 2) / np.cos(phi) - n
+        iterations += 1
+        if iterations > 100:
+            break
+    return phi * (180 / np.pi), lambda_ * (180 / np.pi), h
+
+
+def nav_solve(abs_sample, prn, sub_frame_start, ready, eph, tow, ms_to_process, samples_per_code,
+              nav_sol_period=500.0, elevation_mask=10.0, use_trop_corr=True, start_offset=68.802,
+              c=299792458.0):
+    """The measurement loop of postNavigate (postNavigation.py:159-301) for one recording.
+
+    ``abs_sample[ch]``: absoluteSample series; ``prn[ch]``; ``sub_frame_start[ch]`` (0 for channels
+    without a preamble); ``ready``: channel indices with a decoded ephemeris (readyChnList, :166);
+    ``eph[prn-1]``: mapping with EPH_FIELDS; ``tow``: transmitTime of the first epoch (:168).
+    Returns a dict of arrays with one column per measurement epoch."""
+    n_ch = len(prn)
+    sub_frame_start = np.asarray(sub_frame_start)
+    ready = np.asarray(ready, dtype=int)
+    prn = np.asarray(prn)
+    n_ep = int(np.fix(ms_to_process - sub_frame_start.max()) / nav_sol_period)          # :199
+    nan = np.nan
+    out = dict(PRN=np.zeros((n_ch, n_ep)), el=nan * np.ones((n_ch, n_ep)), az=nan * np.ones((n_ch, n_ep)),
+               rawP=nan * np.ones((n_ch, n_ep)), correctedP=nan * np.ones((n_ch, n_ep)),
+               DOP=np.zeros((5, n_ep)), X=nan * np.ones(n_ep), Y=nan * np.ones(n_ep), Z=nan * np.ones(n_ep),
+               dt=nan * np.ones(n_ep), latitude=nan * np.ones(n_ep), longitude=nan * np.ones(n_ep),
+               height=nan * np.ones(n_ep), satPositions=nan * np.ones((n_ch, n_ep, 3)),
+               satClkCorr=nan * np.ones((n_ch, n_ep)), n_epochs=n_ep)
+    sat_elev = np.inf * np.ones(n_ch)                                        # :159
+    transmit_time = tow                                                      # :168
+    for m in range(n_ep):
+        with np.errstate(invalid="ignore"):
+            active = np.intersect1d((sat_elev >= elevation_mask).nonzero()[0], ready)   # :201
+        out["PRN"][active, m] = prn[active]                                  # :203
+        out["rawP"][:, m] = calculate_pseudoranges(abs_sample, sub_frame_start + nav_sol_period * m, active,
+                                                   n_ch, samples_per_code, start_offset, c)   # :212-214
+        sat_positions, sat_clk = satpos(transmit_time, prn[active], eph)     # :217
+        out["satPositions"][active, m, :] = sat_positions.T
+        out["satClkCorr"][active, m] = sat_clk
+        if active.size > 3:                                                  # :222
+            xyzdt, el, az, dop = least_square_pos(sat_positions, out["rawP"][active, m] + sat_clk * c, c,
+                                                  use_trop_corr)             # :224-231
+            out["el"][active, m] = el
+            out["az"][active, m] = az
+            out["DOP"][:, m] = dop
+            out["X"][m], out["Y"][m], out["Z"][m], out["dt"][m] = xyzdt
+            sat_elev = out["el"][:, m]                                       # :241
+            out["correctedP"][active, m] = out["rawP"][active, m] + sat_clk * c + out["dt"][m]   # :243-245
+            out["latitude"][m], out["longitude"][m], out["height"][m] = cart2geo(out["X"][m], out["Y"][m],
+                                                                                out["Z"][m], 4)   # :249-254
+        else:                                                                # :264-291
+            out["DOP"][:, m] = 0.0
+            out["az"][active, m] = nan
+            out["el"][active, m] = nan
+        transmit_time += nav_sol_period / 1000                               # :298
+    return out

@@ -144,3 +144,41 @@ def build_pseudo_case(n_ch=8, ms=2000, n_epochs=6, seed=77):
     active[3, :] = 0                                                           # empty list: all inf - inf = nan
     active[4, 1:] = 0                                                          # a single channel
     return abs_sample, ms_index, active
+
+
+# ---------------------------------------------------------------------------------------------
+# Navigation-solution cases (second half).  The float inputs (ephemerides,
+# polynomial coefficients of the code-period arrival samples) are stored in tests/golden/nav.npz by
+# tests/golden/make_golden_nav.py; the absoluteSample series are expanded from them with integer arithmetic.
+# ---------------------------------------------------------------------------------------------
+NAV_MS = 37000
+NAV_FIELDS = ("t_oc", "a_f2", "a_f1", "a_f0", "T_GD", "sqrtA", "t_oe", "deltan", "M_0", "e", "omega",
+              "C_uc", "C_us", "C_rc", "C_rs", "i_0", "iDot", "C_ic", "C_is", "omega_0", "omegaDot")
+
+
+def nav_abs_sample(coef, n_code=38192, ms=NAV_MS):
+    """coef int64 [C][4] = (b, k0, p1, p2): absoluteSample[i] = b + k*n_code + ((p1*k + p2*k*k) >> 40), k = i - k0."""
+    coef = np.asarray(coef, dtype=np.int64)
+    i = np.arange(ms, dtype=np.int64)[None, :]
+    k = i - coef[:, 1:2]
+    return (coef[:, 0:1] + k * n_code + ((coef[:, 2:3] * k + coef[:, 3:4] * k * k) >> 40)).astype(np.float64)
+
+
+def load_nav_cases():
+    """List of dicts (one per golden recording): inputs of the measurement loop + the reference's outputs."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "nav.npz"))
+    cases = []
+    for r in range(int(z["n_cases"])):
+        g = lambda name: z["c%d_%s" % (r, name)]
+        eph_arr = g("eph_arr")                                                # [C][21] in NAV_FIELDS order
+        prn = g("prn")
+        eph = [None] * 32
+        for c in range(len(prn)):
+            eph[int(prn[c]) - 1] = dict(zip(NAV_FIELDS, eph_arr[c]))
+        cases.append(dict(coef=g("coef"), prn=prn, eph_arr=eph_arr, eph=eph, sub_frame_start=g("sub_frame_start"),
+                          ready=g("ready"), tow=float(g("tow")), elevation_mask=float(g("elevation_mask")),
+                          use_trop_corr=bool(g("use_trop_corr")), rx=g("rx"),
+                          ref={k: g("ref_" + k) for k in ("rawP", "el", "az", "correctedP", "DOP", "X", "Y", "Z", "dt",
+                                                          "latitude", "longitude", "height", "PRN")}))
+    return cases
