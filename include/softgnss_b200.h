@@ -173,6 +173,53 @@ int sgx_pseudoranges(const double* track_out, int32_t n_recordings, int32_t n_ch
                      double samples_per_code, double start_offset, double c, double* pseudoranges,
                      void* cuda_stream);
 
+/* ---- navigation solution (second half) -------------------------------------- */
+/* Broadcast-ephemeris terms read by geoFunctions.satpos (geoFunctions/__init__.py:779-885), one per channel,
+ * in the units ephemeris.py decodes them to (seconds, radians, metres). */
+typedef struct sgx_eph {
+  double t_oc, a_f2, a_f1, a_f0, T_GD;
+  double sqrtA, t_oe, deltan, M_0, e, omega;
+  double C_uc, C_us, C_rc, C_rs;
+  double i_0, iDot, C_ic, C_is, omega_0, omegaDot;
+} sgx_eph;
+
+/* Settings read by the measurement loop: settings.samplesPerCode, .startOffset, .c, .navSolPeriod,
+ * .elevationMask, .useTropCorr (initialize.py:144-181). */
+typedef struct sgx_nav_settings {
+  double samples_per_code, start_offset, c, nav_sol_period, elevation_mask;
+  int32_t use_trop_corr, reserved;
+} sgx_nav_settings;
+
+#define SGX_NAV_SOL_FIELDS 12   /* X Y Z dt GDOP PDOP HDOP VDOP TDOP latitude longitude height */
+
+/* Replaces the measurement loop of NavigationResult.postNavigate (postNavigation.py:159-301) with the
+ * functions it calls -- calculatePseudoranges (:27-72), geoFunctions.satpos (geoFunctions/__init__.py:779-885),
+ * leastSquarePos (:636-739; e_r_corr :491, topocent :1003, togeod :892, tropo :1071) and cart2geo (:7-77) --
+ * batched over independent recordings (one warp per recording, lane = channel; epochs are sequential because
+ * the elevation mask of an epoch uses the elevations of the epoch before, :201/:241).  UTM conversion
+ * (findUtmZone, cart2utm) and ephemeris decoding stay with the caller.
+ *   abs_sample       double: the absoluteSample series of channel (r, c) starts at abs_sample + (r*n_channels + c)*stride
+ *                    and holds ms values (sgx_track's output: pointer to its first element, stride = SGX_TRACK_FIELDS*ms;
+ *                    host or device)
+ *   sub_frame_start  int32 [R][C]   subFrameStart of findPreambles (0: none)
+ *   ready            uint8 [R][C]   1 = channel is in readyChnList (preamble found and ephemeris decoded, :166)
+ *   eph              sgx_eph [R][C] ephemeris of the channel's PRN (read for ready channels only)
+ *   tow              double [R]     transmitTime of the first measurement (:168)
+ *   n_epochs         int32 [R]      int(fix(msToProcess - max(subFrameStart)) / navSolPeriod) (:199); epochs beyond
+ *                                   it keep the reference's initial values (NaN, DOP 0)
+ * Outputs (host or device, same kind as `sol`), E = max_epochs:
+ *   raw_p, corrected_p, el, az  double [R][E][C]  channel[0].rawP / .correctedP / .el / .az (:212, :243, :227)
+ *   sat_pos   double [R][E][C][3], sat_clk double [R][E][C]: satpos outputs per listed channel (optional, may be NULL)
+ *   active    uint8 [R][E][C]   1 = channel was in activeChnList of that epoch (channel[0].PRN != 0)
+ *   sol       double [R][E][SGX_NAV_SOL_FIELDS]: X Y Z dt (NaN without a fix), DOP[5] (0 without a fix), latitude,
+ *             longitude (degrees), height
+ * Float64 throughout; agrees with the reference to 1e-5 m on the fix (pseudoranges are bit-identical). */
+int sgx_nav_solve(const double* abs_sample, int64_t stride, int32_t n_recordings, int32_t n_channels, int32_t ms,
+                  const int32_t* sub_frame_start, const uint8_t* ready, const sgx_eph* eph, const double* tow,
+                  const int32_t* n_epochs, int32_t max_epochs, const sgx_nav_settings* st, double* raw_p,
+                  double* corrected_p, double* el, double* az, double* sat_pos, double* sat_clk, uint8_t* active,
+                  double* sol, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,7 +20,7 @@ SGX_ERR_SHORT = -3
 
 EXPORTS = ("sgx_abi_version", "sgx_last_error", "sgx_device_count", "sgx_set_device",
            "sgx_kernel_launch_count", "sgx_acquire", "sgx_track", "sgx_synth_generate", "sgx_fft_c2c",
-           "sgx_find_preambles", "sgx_pseudoranges")
+           "sgx_find_preambles", "sgx_pseudoranges", "sgx_nav_solve")
 
 
 class NativeError(RuntimeError):
@@ -32,6 +32,17 @@ class NativeError(RuntimeError):
 class SgxChannel(ctypes.Structure):
     _fields_ = [("prn", ctypes.c_int32), ("reserved", ctypes.c_int32),
                 ("acquiredFreq", ctypes.c_double), ("codePhase", ctypes.c_double)]
+
+
+EPH_FIELDS = ("t_oc", "a_f2", "a_f1", "a_f0", "T_GD", "sqrtA", "t_oe", "deltan", "M_0", "e", "omega",
+              "C_uc", "C_us", "C_rc", "C_rs", "i_0", "iDot", "C_ic", "C_is", "omega_0", "omegaDot")   # sgx_eph, in order
+NAV_SOL_FIELDS = ("X", "Y", "Z", "dt", "GDOP", "PDOP", "HDOP", "VDOP", "TDOP", "latitude", "longitude", "height")
+
+
+class SgxNavSettings(ctypes.Structure):
+    _fields_ = [("samples_per_code", ctypes.c_double), ("start_offset", ctypes.c_double), ("c", ctypes.c_double),
+                ("nav_sol_period", ctypes.c_double), ("elevation_mask", ctypes.c_double),
+                ("use_trop_corr", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 class SgxSynthSpec(ctypes.Structure):
@@ -141,6 +152,34 @@ class Lib(object):
         self.check(self.dll.sgx_pseudoranges(_ptr(track_out), n_rec, n_ch, int(ms), _ptr(ms_index), _ptr(active), n_ep,
                                              float(samples_per_code), float(start_offset), float(c), _ptr(out),
                                              ctypes.c_void_p(stream)))
+        return out
+
+    def nav_solve(self, abs_sample, stride, n_rec, n_ch, ms, sub_frame_start, ready, eph, tow, n_epochs, nav_settings,
+                  want_sat=True, stream=0):
+        """abs_sample: float64 numpy array / CUDA tensor whose channel rows are `stride` apart; sub_frame_start int32 /
+        ready uint8 [n_rec][n_ch]; eph float64 [n_rec][n_ch][21] (EPH_FIELDS order); tow float64 [n_rec]; n_epochs
+        int32 [n_rec].  Returns a dict of numpy arrays with the epoch axis second ([R][E][C] / [R][E][12])."""
+        self.require_device()
+        sub_frame_start = np.ascontiguousarray(sub_frame_start, dtype=np.int32).reshape(n_rec, n_ch)
+        ready = np.ascontiguousarray(ready, dtype=np.uint8).reshape(n_rec, n_ch)
+        eph = np.ascontiguousarray(eph, dtype=np.float64).reshape(n_rec, n_ch, len(EPH_FIELDS))
+        tow = np.ascontiguousarray(tow, dtype=np.float64).reshape(n_rec)
+        n_epochs = np.ascontiguousarray(n_epochs, dtype=np.int32).reshape(n_rec)
+        e_max = int(n_epochs.max()) if n_rec else 0
+        shp = (n_rec, e_max, n_ch)
+        out = dict(rawP=np.empty(shp), correctedP=np.empty(shp), el=np.empty(shp), az=np.empty(shp),
+                   satPositions=np.empty(shp + (3,)) if want_sat else None, satClkCorr=np.empty(shp) if want_sat else None,
+                   active=np.empty(shp, dtype=np.uint8), sol=np.empty((n_rec, e_max, len(NAV_SOL_FIELDS))))
+        vp, i32 = ctypes.c_void_p, ctypes.c_int32
+        self.dll.sgx_nav_solve.argtypes = [vp, ctypes.c_int64, i32, i32, i32, vp, vp, vp, vp, vp, i32,
+                                           ctypes.POINTER(SgxNavSettings), vp, vp, vp, vp, vp, vp, vp, vp, vp]
+        self.check(self.dll.sgx_nav_solve(_ptr(abs_sample), int(stride), n_rec, n_ch, int(ms), _ptr(sub_frame_start),
+                                          _ptr(ready), _ptr(eph), _ptr(tow), _ptr(n_epochs), e_max,
+                                          ctypes.byref(nav_settings), _ptr(out["rawP"]), _ptr(out["correctedP"]),
+                                          _ptr(out["el"]), _ptr(out["az"]), _ptr(out["satPositions"]),
+                                          _ptr(out["satClkCorr"]), _ptr(out["active"]), _ptr(out["sol"]),
+                                          ctypes.c_void_p(stream)))
+        out["n_epochs"] = n_epochs
         return out
 
     # ------------------------------------------------------------------ synthetic recordings

@@ -91,6 +91,81 @@ def pseudoranges_batch(track_out, ms_index, active, settings, stream=0):
                                       settings.startOffset, settings.c, stream=stream)
 
 
+def nav_settings(settings):
+    """The settings the measurement loop reads (initialize.py:144-181) as the C-ABI struct."""
+    return _native.SgxNavSettings(float(settings.samplesPerCode), float(settings.startOffset), float(settings.c),
+                                  float(settings.navSolPeriod), float(settings.elevationMask),
+                                  int(bool(settings.useTropCorr)), 0)
+
+
+def nav_epochs(settings, sub_frame_start):
+    """Number of measurement epochs, postNavigation.py:199."""
+    return int(np.fix(settings.msToProcess - np.max(sub_frame_start)) / settings.navSolPeriod)
+
+
+def nav_solve_batch(abs_sample, sub_frame_start, ready, eph, tow, settings, stride=None, ms=None, want_sat=True,
+                    stream=0):
+    """Measurement loops of R independent recordings in one launch (postNavigation.py:159-301).
+
+    ``abs_sample``: float64 ``[R, C, ms]`` numpy array, or ``track_batch``'s ``[R, C, 13, ms]`` output (numpy or CUDA
+    tensor; field 0 is read in place); ``sub_frame_start`` / ``ready`` ``[R, C]``; ``eph`` ``[R, C, 21]`` in
+    ``_native.EPH_FIELDS`` order (row c = ephemeris of channel c's PRN); ``tow`` ``[R]``.
+    Returns a dict: ``rawP, correctedP, el, az, active`` ``[R, E, C]``, ``satPositions`` ``[R, E, C, 3]``,
+    ``satClkCorr``, ``sol`` ``[R, E, 12]`` (``_native.NAV_SOL_FIELDS``), ``n_epochs`` ``[R]``."""
+    shape = tuple(abs_sample.shape)
+    r, c = shape[0], shape[1]
+    if ms is None:
+        ms = shape[-1]
+    if stride is None:
+        stride = int(np.prod(shape[2:]))
+    sub_frame_start = np.asarray(sub_frame_start).reshape(r, c)
+    n_ep = np.array([nav_epochs(settings, sub_frame_start[i]) for i in range(r)], dtype=np.int32)
+    if isinstance(abs_sample, np.ndarray):
+        abs_sample = np.ascontiguousarray(abs_sample, dtype=np.float64)
+    return _native.lib().nav_solve(abs_sample, stride, r, c, ms, sub_frame_start, ready, eph, tow, n_ep,
+                                   nav_settings(settings), want_sat=want_sat, stream=stream)
+
+
+def eph_rows(eph, prn):
+    """Rows of ``_native.EPH_FIELDS`` for the channels' PRNs from the reference's ephemeris recarray
+    (postNavigation.py:120-140: ``eph[PRN - 1].<field>``); channels without an ephemeris get zeros."""
+    rows = np.zeros((len(prn), len(_native.EPH_FIELDS)))
+    for ch, p in enumerate(prn):
+        if p <= 0:
+            continue
+        rec = eph[int(p) - 1]
+        vals = [rec[k] if isinstance(rec, dict) else getattr(rec, k) for k in _native.EPH_FIELDS]
+        if all(v is not None for v in vals):
+            rows[ch] = vals
+    return rows
+
+
+def navSolutions(trackResults, subFrameStart, readyChnList, eph, TOW, settings):
+    """The measurement loop of ``postNavigate`` for one recording in the reference's own result layout
+    (postNavigation.py:176-197): returns (navSolutions, channel) -- ``navSolutions.X/Y/Z/dt/latitude/longitude/
+    height`` of length E, ``.DOP`` ``[5, E]``; ``channel.PRN/el/az/rawP/correctedP`` ``[numberOfChannels, E]``.
+    UTM fields (``E, N, U, utmZone``) are left to the reference's ``cart2utm``."""
+    n_ch = settings.numberOfChannels
+    ms = len(trackResults[0].absoluteSample)
+    abs_sample = np.zeros((1, n_ch, ms))
+    prn = np.zeros(n_ch, dtype=np.int64)
+    for c in range(min(n_ch, len(trackResults))):
+        abs_sample[0, c] = trackResults[c].absoluteSample
+        prn[c] = trackResults[c].PRN
+    ready = np.zeros((1, n_ch), dtype=np.uint8)
+    ready[0, np.asarray(readyChnList, dtype=int)] = 1
+    out = nav_solve_batch(abs_sample, np.asarray(subFrameStart)[None, :n_ch], ready, eph_rows(eph, prn)[None],
+                          [float(TOW)], settings)
+    sol = out["sol"][0]
+    channel = np.rec.array([(np.where(out["active"][0].T > 0, prn[:, None], 0).astype(np.float64), out["el"][0].T.copy(),
+                             out["az"][0].T.copy(), out["rawP"][0].T.copy(), out["correctedP"][0].T.copy())],
+                           formats=['O'] * 5, names='PRN,el,az,rawP,correctedP')
+    nav = np.rec.array([(channel, sol[:, 4:9].T.copy(), sol[:, 0].copy(), sol[:, 1].copy(), sol[:, 2].copy(),
+                         sol[:, 3].copy(), sol[:, 9].copy(), sol[:, 10].copy(), sol[:, 11].copy())],
+                       formats=['O'] * 9, names='channel,DOP,X,Y,Z,dt,latitude,longitude,height')
+    return nav, channel
+
+
 def install(navigation_result_cls):
     """Bind the B200 preamble search into the reference's own class:
     ``NavigationResult.findPreambles`` keeps its signature and return value."""

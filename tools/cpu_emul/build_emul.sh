@@ -6,7 +6,7 @@ HERE=$(cd "$(dirname "$0")" && pwd)
 ROOT=$(cd "$HERE/../.." && pwd)
 SRC=$ROOT/softgnss_python_b200/csrc
 FILES=""
-for f in sgx_api.cu sgx_track.cu sgx_synth.cu sgx_acq.cu sgx_bitsync.cu; do
+for f in sgx_api.cu sgx_track.cu sgx_synth.cu sgx_acq.cu sgx_bitsync.cu sgx_nav.cu; do
   [ -f "$SRC/$f" ] && FILES="$FILES $SRC/$f"
 done
 g++ -x c++ -std=c++17 -O2 -g -DSGX_EMUL -ffp-contract=off -fPIC -shared -pthread \
