@@ -14,6 +14,8 @@ Primary line  : tracking channel-ms/s on BASELINE.json config 4 ("batched tracki
                 timed region.
 `secondary`   : acquisition search cells/s (config 1 settings, a batch of 11 ms recordings per GPU).
 `tertiary`    : preamble search / nav-bit summation on the tracking result, channels/s.
+`quaternary`  : navigation solution (pseudoranges, satellite positions, least-squares fix per measurement epoch;
+                SURVEY.md 8(f) row 4) for one recording per tracked recording of the shard, fixes/s.
 `roofline`    : tracking kernel, algorithmic bytes (38192 B in + 104 B out per channel-ms,
                 SURVEY.md section 8(d)) / CUDA-event duration vs the measured HBM copy bandwidth.
 `cpu_baseline`: the numpy oracle (a restatement of the reference's loops, oracle/gnss_oracle.py) timed
@@ -345,6 +347,56 @@ def run_gpu(args, rank, world):
                                                % (CHANNELS, ms)}
             assert np.array_equal(of, first[:CHANNELS]), "bit sync differs from the oracle"
 
+    # ---- quaternary: measurement loop of postNavigate on the device (8(f) row 4) --------------------------
+    navb = None
+    if not args.no_acq:
+        from softgnss_python_b200 import postnav
+        from tests.cases import NAV_MS, load_nav_cases, nav_abs_sample     # committed input vectors (not the oracle)
+        from tests import nav_util
+        ncases = load_nav_cases()
+        ns = nav_util.settings_for(ncases[0], CHANNELS, NAV_MS)
+        nrec = recs
+        n_in = [nav_util.case_inputs(ncases[r % len(ncases)]) for r in range(nrec)]
+        n_abs = torch.from_numpy(np.stack([nav_abs_sample(ncases[r % len(ncases)]["coef"]) + 38192.0 * r
+                                           for r in range(nrec)])).cuda()
+        n_args = (n_abs, np.stack([x[0] for x in n_in]), np.stack([x[1] for x in n_in]), np.stack([x[2] for x in n_in]),
+                  [ncases[r % len(ncases)]["tow"] for r in range(nrec)], ns)
+        for _ in range(args.warmup):
+            postnav.nav_solve_batch(*n_args, stream=stream)
+        barrier()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ql0 = L.launches()
+        q0.record()
+        for _ in range(args.steps):
+            nout = postnav.nav_solve_batch(*n_args, stream=stream)
+        q1.record()
+        barrier()
+        tq = torch.tensor([q0.elapsed_time(q1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tq, op=dist.ReduceOp.MAX)
+        q_ms = float(tq.item()) / args.steps
+        n_fix = int(nout["n_epochs"].sum())
+        navb = {"metric": "navigation epochs/s", "value": world * n_fix / (q_ms / 1e3), "unit": "epochs/s",
+                "ms_per_step": q_ms, "gpu_launches": int(L.launches() - ql0),
+                "config": {"workload": "%d recordings x %d channels x %d measurement epochs per GPU: pseudoranges, satpos, "
+                                       "7-iteration least-squares fix with tropospheric correction, DOP, cart2geo; "
+                                       "absoluteSample resident on the device, results copied to the host inside the "
+                                       "timed region" % (nrec, CHANNELS, int(nout["n_epochs"][0])),
+                           "epochs_with_fix": int(np.isfinite(nout["sol"][:, :, 0]).sum())},
+                "roofline": {"bound": "latency (one warp per recording, epochs sequential through the elevation mask; "
+                                      "float64 dependency chain)", "frac": None}}
+        if rank == 0 and not args.no_cpu:
+            from oracle import gnss_oracle as orc
+            c0_ = ncases[0]
+            t0 = time.perf_counter()
+            o = orc.nav_solve(nav_abs_sample(c0_["coef"]), c0_["prn"], c0_["sub_frame_start"], c0_["ready"], c0_["eph"],
+                              c0_["tow"], float(NAV_MS), 38192, elevation_mask=ns.elevationMask, use_trop_corr=ns.useTropCorr)
+            dt = time.perf_counter() - t0
+            navb["cpu_baseline"] = {"value": o["n_epochs"] / dt, "unit": "epochs/s", "cores": 1, "kind": "port",
+                                    "sample": "1 recording x 8 channels x %d epochs, oracle/gnss_oracle.py nav_solve "
+                                              "(bit-identical to the reference's loop)" % o["n_epochs"]}
+            nav_util.compare_nav(nout, 0, o, "bench nav solve")
+
     ck = clocks.stop(c0, c1) if clocks else None
     if world > 1:
         counts = [None] * world
@@ -378,6 +430,7 @@ def run_gpu(args, rank, world):
         "clocks": ck,
         "secondary": acq,
         "tertiary": bsync,
+        "quaternary": navb,
     }
     if not args.no_cpu:
         line["cpu_baseline"] = cpu_track_baseline(TRACK_CPU_MS, 1)

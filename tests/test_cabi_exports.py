@@ -32,6 +32,7 @@ def test_struct_layouts_match_header(lib):
     assert ctypes.sizeof(_native.SgxChannel) == 24
     assert ctypes.sizeof(SgxSettings) == 13 * 8 + 8 + 10 * 4
     assert ctypes.sizeof(_native.SgxSynthSpec) == 8 + 4 * 4 + 3 * 12 * 4 + 4 * 12 * 8
+    assert ctypes.sizeof(_native.SgxNavSettings) == 5 * 8 + 2 * 4 and len(_native.EPH_FIELDS) == 21   # sgx_eph: 21 doubles
 
 
 def test_no_cpu_fallback(lib):
@@ -47,3 +48,9 @@ def test_no_cpu_fallback(lib):
     ch = np.rec.fromarrays([[1], [9.548e6], [0.0], ['T']], names="PRN,acquiredFreq,codePhase,status")
     with pytest.raises(_native.NativeError):
         tracking(np.zeros(3 * 38192, dtype=np.int8), ch, Settings(numberOfChannels=1, msToProcess=1.0))
+    from softgnss_python_b200 import postnav
+    with pytest.raises(_native.NativeError):
+        postnav.find_preambles_batch(np.ones((1, 8000)))
+    s = Settings(numberOfChannels=4, msToProcess=2000.0)
+    with pytest.raises(_native.NativeError):
+        postnav.nav_solve_batch(np.zeros((1, 4, 2000)), np.zeros((1, 4)), np.ones((1, 4)), np.zeros((1, 4, 21)), [0.0], s)
