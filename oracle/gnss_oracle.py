@@ -675,3 +675,57 @@ def nav_solve(abs_sample, prn, sub_frame_start, ready, eph, tow, ms_to_process, 
             out["el"][active, m] = nan
         transmit_time += nav_sol_period / 1000                               # :298
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Ephemeris decoding (ephemeris.py:98-196): the host-side stage between the preamble search and the
+# measurement loop.  Integer restatement on 0/1 arrays (the reference slices character strings).
+# ---------------------------------------------------------------------------------------------
+EPH_ALL = ("weekNumber", "accuracy", "health", "T_GD", "IODC", "t_oc", "a_f2", "a_f1", "a_f0", "IODE_sf2", "C_rs",
+           "deltan", "M_0", "C_uc", "e", "C_us", "sqrtA", "t_oe", "C_ic", "omega_0", "C_is", "i_0", "C_rc", "omega",
+           "omegaDot", "IODE_sf3", "iDot")                                    # ephemeris.py:191-194, in order
+
+
+def _u(b):
+    return int("".join(str(int(x)) for x in b), 2)                          # bin2dec, ephemeris.py:1-8
+
+
+def _s(b):
+    v = _u(b)                                                               # twosComp2dec, ephemeris.py:30-41
+    return v - (1 << len(b)) if int(b[0]) == 1 else v
+
+
+def ephemeris(bits, d30star):
+    """ephemeris.py:98-196.  ``bits``: 1500 values 0/1 (five subframes from a subframe start), ``d30star``:
+    the bit before them.  Returns (dict with EPH_ALL keys -- None for fields whose subframe is absent --, TOW)."""
+    bits = [int(b) for b in bits]
+    assert len(bits) >= 1500
+    gps_pi = 3.1415926535898                                                 # :113
+    d30 = int(d30star)
+    out = dict.fromkeys(EPH_ALL)
+    sf = None
+    for i in range(5):
+        sf = bits[300 * i:300 * (i + 1)]
+        for j in range(10):                                                  # :122-127 checkPhase: data bits inverted by D30*
+            if d30 == 1:
+                for k in range(30 * j, 30 * j + 24):
+                    sf[k] ^= 1
+            d30 = sf[30 * j + 29]
+        sid = _u(sf[49:52])                                                  # :133
+        if sid == 1:                                                         # :139-150
+            out.update(weekNumber=_u(sf[60:70]) + 1024, accuracy=_u(sf[72:76]), health=_u(sf[76:82]),
+                       T_GD=_s(sf[195:204]) * 2 ** (-31), IODC=_u(sf[82:84] + sf[196:204]), t_oc=_u(sf[218:234]) * 2 ** 4,
+                       a_f2=_s(sf[240:248]) * 2 ** (-55), a_f1=_s(sf[248:264]) * 2 ** (-43), a_f0=_s(sf[270:292]) * 2 ** (-31))
+        elif sid == 2:                                                       # :152-163
+            out.update(IODE_sf2=_u(sf[60:68]), C_rs=_s(sf[68:84]) * 2 ** (-5), deltan=_s(sf[90:106]) * 2 ** (-43) * gps_pi,
+                       M_0=_s(sf[106:114] + sf[120:144]) * 2 ** (-31) * gps_pi, C_uc=_s(sf[150:166]) * 2 ** (-29),
+                       e=_u(sf[166:174] + sf[180:204]) * 2 ** (-33), C_us=_s(sf[210:226]) * 2 ** (-29),
+                       sqrtA=_u(sf[226:234] + sf[240:264]) * 2 ** (-19), t_oe=_u(sf[270:286]) * 2 ** 4)
+        elif sid == 3:                                                       # :165-176
+            out.update(C_ic=_s(sf[60:76]) * 2 ** (-29), omega_0=_s(sf[76:84] + sf[90:114]) * 2 ** (-31) * gps_pi,
+                       C_is=_s(sf[120:136]) * 2 ** (-29), i_0=_s(sf[136:144] + sf[150:174]) * 2 ** (-31) * gps_pi,
+                       C_rc=_s(sf[180:196]) * 2 ** (-5), omega=_s(sf[196:204] + sf[210:234]) * 2 ** (-31) * gps_pi,
+                       omegaDot=_s(sf[240:264]) * 2 ** (-43) * gps_pi, IODE_sf3=_u(sf[270:278]),
+                       iDot=_s(sf[278:292]) * 2 ** (-43) * gps_pi)
+    tow = _u(sf[30:47]) * 6 - 30                                             # :190 (HOW of the fifth subframe)
+    return out, tow

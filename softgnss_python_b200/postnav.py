@@ -91,6 +91,72 @@ def pseudoranges_batch(track_out, ms_index, active, settings, stream=0):
                                       settings.startOffset, settings.c, stream=stream)
 
 
+# ---- ephemeris decoding (ephemeris.py:98-196): host-side integer bit slicing between the two device stages ----------
+EPH_ALL = ("weekNumber", "accuracy", "health", "T_GD", "IODC", "t_oc", "a_f2", "a_f1", "a_f0", "IODE_sf2", "C_rs",
+           "deltan", "M_0", "C_uc", "e", "C_us", "sqrtA", "t_oe", "C_ic", "omega_0", "C_is", "i_0", "C_rc", "omega",
+           "omegaDot", "IODE_sf3", "iDot")
+_GPS_PI = 3.1415926535898                      # ephemeris.py:113
+#  field: (subframe ID, bit ranges inside the subframe, signed, power of two, times pi)   -- ephemeris.py:139-176
+_EPH_LAYOUT = {
+    "weekNumber": (1, ((60, 70),), False, 0, False), "accuracy": (1, ((72, 76),), False, 0, False),
+    "health": (1, ((76, 82),), False, 0, False), "T_GD": (1, ((195, 204),), True, -31, False),
+    "IODC": (1, ((82, 84), (196, 204)), False, 0, False), "t_oc": (1, ((218, 234),), False, 4, False),
+    "a_f2": (1, ((240, 248),), True, -55, False), "a_f1": (1, ((248, 264),), True, -43, False),
+    "a_f0": (1, ((270, 292),), True, -31, False),
+    "IODE_sf2": (2, ((60, 68),), False, 0, False), "C_rs": (2, ((68, 84),), True, -5, False),
+    "deltan": (2, ((90, 106),), True, -43, True), "M_0": (2, ((106, 114), (120, 144)), True, -31, True),
+    "C_uc": (2, ((150, 166),), True, -29, False), "e": (2, ((166, 174), (180, 204)), False, -33, False),
+    "C_us": (2, ((210, 226),), True, -29, False), "sqrtA": (2, ((226, 234), (240, 264)), False, -19, False),
+    "t_oe": (2, ((270, 286),), False, 4, False),
+    "C_ic": (3, ((60, 76),), True, -29, False), "omega_0": (3, ((76, 84), (90, 114)), True, -31, True),
+    "C_is": (3, ((120, 136),), True, -29, False), "i_0": (3, ((136, 144), (150, 174)), True, -31, True),
+    "C_rc": (3, ((180, 196),), True, -5, False), "omega": (3, ((196, 204), (210, 234)), True, -31, True),
+    "omegaDot": (3, ((240, 264),), True, -43, True), "IODE_sf3": (3, ((270, 278),), False, 0, False),
+    "iDot": (3, ((278, 292),), True, -43, True),
+}
+
+
+def _field(sf, ranges, signed):
+    v, n = 0, 0
+    for lo, hi in ranges:
+        for b in sf[lo:hi]:
+            v = (v << 1) | int(b)
+        n += hi - lo
+    if signed and v >> (n - 1):
+        v -= 1 << n
+    return v
+
+
+def ephemeris(bits, d30star):
+    """``ephemeris.ephemeris(bits, D30Star)`` of the reference (ephemeris.py:98-196) on hard bits: ``bits`` holds
+    1500 values 0/1 (or the characters '0'/'1') starting at a subframe boundary, ``d30star`` the bit before them.
+    Returns (dict keyed by ``EPH_ALL``, TOW); fields of a subframe ID that does not occur stay ``None`` (the
+    reference raises ``UnboundLocalError`` there, the caller's ``is None`` checks at postNavigation.py:142-146
+    are what they feed)."""
+    b = np.array([int(x) for x in bits[:1500]], dtype=np.uint8)
+    if b.size < 1500:
+        raise TypeError('The parameter BITS must contain 1500 bits!')                      # ephemeris.py:101
+    words = b.reshape(50, 30).copy()
+    prev = np.concatenate([[int(d30star)], words[:-1, 29]])                                 # parity bits are never inverted
+    words[:, :24] ^= prev[:, None].astype(np.uint8)                                         # checkPhase, :122-127
+    out = dict.fromkeys(EPH_ALL)
+    for i in range(5):
+        sf = words[10 * i:10 * i + 10].reshape(300)
+        sid = _field(sf, ((49, 52),), False)                                                # :133
+        for name, (fid, ranges, signed, p2, pi) in _EPH_LAYOUT.items():
+            if fid == sid:
+                v = _field(sf, ranges, signed)
+                if name == "weekNumber":
+                    v += 1024                                                                # :139
+                if p2 or pi:
+                    v = v * 2 ** p2
+                    if pi:
+                        v = v * _GPS_PI
+                out[name] = v
+    tow = _field(words[40:50].reshape(300), ((30, 47),), False) * 6 - 30                     # :190
+    return out, tow
+
+
 def nav_settings(settings):
     """The settings the measurement loop reads (initialize.py:144-181) as the C-ABI struct."""
     return _native.SgxNavSettings(float(settings.samplesPerCode), float(settings.startOffset), float(settings.c),

@@ -182,3 +182,31 @@ def load_nav_cases():
                           ref={k: g("ref_" + k) for k in ("rawP", "el", "az", "correctedP", "DOP", "X", "Y", "Z", "dt",
                                                           "latitude", "longitude", "height", "PRN")}))
     return cases
+
+
+# ---------------------------------------------------------------------------------------------
+# Ephemeris-decoding cases: 1501 hard bits (bit 0 = D30* of the word before the first subframe)
+# ---------------------------------------------------------------------------------------------
+def build_ephemeris_cases():
+    """uint8 [n][1501].  Rows 0-4: LNAV streams of navsynth's encoder (one per starting subframe ID, alternating
+    polarity of the preceding bit); rows 5-9: hash-random bits with the subframe IDs forced to 1..5 in rotation, so
+    that every field (clock terms, T_GD, IODC, signs) takes arbitrary values."""
+    from softgnss_python_b200 import navsynth
+    rows = []
+    for k in range(5):
+        e = dict(sqrtA=5153.6 + 0.1 * k, e=0.002 + 0.001 * k, i_0=np.radians(54.0 + k), omega_0=-2.5 + 1.2 * k,
+                 omega=2.9 - 1.4 * k, M_0=-3.0 + 1.5 * k, omegaDot=-8.0e-9 * (k - 2), iDot=1e-10 * (k - 2), deltan=1.5e-9 * (k - 1),
+                 t_oe=388800.0 + 16 * k, weekNumber=2100 + k, IODE=10 + k, C_rs=-50.0 + 30 * k, C_rc=200.0 - 90 * k,
+                 C_uc=1e-6 * (k - 2), C_us=-2e-6 * (k - 1), C_ic=5e-8 * (k - 3), C_is=-4e-8 * k)
+        bits = navsynth.encode_stream(navsynth.quantize_ephemeris(e), 1 + k, 388800 - 6, 7)
+        rows.append(bits[299:1800].astype(np.uint8))          # last bit of the first subframe + the five after it
+    for k in range(5):
+        b = (_hash_noise(900 + k, 1501) & 1).astype(np.uint8)
+        for i in range(5):
+            sid = (k + i) % 5 + 1
+            base = 1 + 300 * i
+            inv = b[base + 29]                                 # D30 of word 1 decides the inversion of word 2
+            for j, bit in enumerate(((sid >> 2) & 1, (sid >> 1) & 1, sid & 1)):
+                b[base + 49 + j] = bit ^ inv
+        rows.append(b)
+    return np.stack(rows)

@@ -87,10 +87,14 @@ def run_reference(ref, case):
         e = dict(zip(NAV_FIELDS, case["eph_arr"][c]))
         e.update(weekNumber=1076, accuracy=0, health=0, IODC=1, IODE_sf2=1, IODE_sf3=1)
         return tuple(e[k] for k in EPH_NAMES), case["tow"]
+    real_ephemeris = ref["postNavigation"].ephemeris.ephemeris
     ref["postNavigation"].ephemeris.ephemeris = fake_ephemeris
-    with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
-        warnings.simplefilter("ignore")
-        nav.postNavigate()
+    try:
+        with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            nav.postNavigate()
+    finally:
+        ref["postNavigation"].ephemeris.ephemeris = real_ephemeris
     sol = nav.solutions[0]
     n_ep = int(np.fix(NAV_MS - case["sub_frame_start"].max()) / s.navSolPeriod)
     out = {k: np.array(getattr(sol.channel[0], k)[:, :n_ep], dtype=np.float64) for k in ("rawP", "el", "az", "correctedP", "PRN")}
@@ -134,6 +138,24 @@ def main():
                  np.nanmedian(err) if np.isfinite(err).any() else np.nan, (out["PRN"] > 0).sum(0)[:4]))
     store["n_cases"] = np.array(len(cases))
     np.savez_compressed(os.path.join(HERE, "nav.npz"), **store)
+    make_ephemeris_golden(ref)
+
+
+def make_ephemeris_golden(ref):
+    """ephemeris.py:98-196 of the reference on the streams of tests/cases.py:build_ephemeris_cases ->
+    tests/golden/ephemeris.npz (27 decoded fields in the reference's order + TOW per stream)."""
+    import hashlib
+    from tests.cases import build_ephemeris_cases
+    rows = build_ephemeris_cases()
+    table = np.zeros((len(rows), 28))
+    for r, row in enumerate(rows):
+        chars = [str(int(b)) for b in row]
+        eph, tow = ref["ephemeris"].ephemeris(chars[1:], chars[0])
+        table[r, :27] = eph
+        table[r, 27] = tow
+    np.savez_compressed(os.path.join(HERE, "ephemeris.npz"), table=table,
+                        input_sha1=hashlib.sha1(rows.tobytes()).hexdigest())
+    print("ephemeris: %d streams, TOW %s" % (len(rows), table[:, 27].astype(int).tolist()))
 
 
 if __name__ == "__main__":

@@ -50,3 +50,23 @@ def test_tropo_and_topocent_known_values():
     assert abs(el - 90.0) < 1e-6 and abs(d - 100.0) < 1e-9
     az, el, d = orc.topocent(np.array([6378137.0, 0.0, 0.0]), np.array([0.0, 0.0, 100.0]))
     assert abs(az) < 1e-9 and abs(el) < 1e-6                                  # due north on the horizon
+
+
+def test_ephemeris_decoder_matches_reference():
+    """oracle.ephemeris and the product's host-side decoder (postnav.ephemeris) against ephemeris.py of the
+    reference (tests/golden/ephemeris.npz): every field and the TOW identical on encoder streams and random bits."""
+    import hashlib
+    import os
+    from softgnss_python_b200 import postnav
+    from tests.cases import build_ephemeris_cases
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ephemeris.npz"))
+    rows = build_ephemeris_cases()
+    assert hashlib.sha1(rows.tobytes()).hexdigest() == str(g["input_sha1"])
+    for r, row in enumerate(rows):
+        for dec in (orc.ephemeris, postnav.ephemeris):
+            eph, tow = dec(row[1:], row[0])
+            assert tow == g["table"][r, 27]
+            assert [eph[k] for k in orc.EPH_ALL] == g["table"][r, :27].tolist(), (r, dec.__module__)
+    # a stream without subframes 1-3 leaves their fields undecoded
+    eph, _ = postnav.ephemeris(np.zeros(1500, dtype=np.uint8), 0)
+    assert eph["IODC"] is None and eph["IODE_sf2"] is None
