@@ -1,5 +1,6 @@
-"""Preamble search and navigation-bit extraction on the B200 -- the first stage of the reference's
-downstream consumer (``postNavigation.py``), SURVEY.md section 8(f) row 3.
+"""The reference's downstream consumer (``postNavigation.py``) on the B200: preamble search and navigation-bit
+extraction, relative pseudoranges, satellite positions and the least-squares
+fix (row 4), with the ephemeris bit-field decoding in between on the host.
 
 Mirrors, with the reference's names and conventions:
 
@@ -200,6 +201,8 @@ def eph_rows(eph, prn):
         if p <= 0:
             continue
         rec = eph[int(p) - 1]
+        if rec is None:
+            continue
         vals = [rec[k] if isinstance(rec, dict) else getattr(rec, k) for k in _native.EPH_FIELDS]
         if all(v is not None for v in vals):
             rows[ch] = vals
@@ -230,6 +233,83 @@ def navSolutions(trackResults, subFrameStart, readyChnList, eph, TOW, settings):
                          sol[:, 3].copy(), sol[:, 9].copy(), sol[:, 10].copy(), sol[:, 11].copy())],
                        formats=['O'] * 9, names='channel,DOP,X,Y,Z,dt,latitude,longitude,height')
     return nav, channel
+
+
+def _decode_channels(bits, valid, first, prn, candidates):
+    """Ephemeris decoding of the channels in ``candidates`` (postNavigation.py:120-146).  Returns
+    (eph list indexed by PRN-1, TOW of the last decoded channel, channels that keep a complete ephemeris)."""
+    eph = [None] * 32
+    tow = None
+    ready = []
+    for ch in candidates:
+        if first[ch] == 0 or not valid[ch]:          # five subframes do not fit after the preamble (the reference raises)
+            continue
+        e, tow = ephemeris(bits[ch][1:], bits[ch][0])                                        # :140
+        eph[int(prn[ch]) - 1] = e
+        if e["IODC"] is None or e["IODE_sf2"] is None or e["IODE_sf3"] is None:              # :142-146
+            continue
+        ready.append(ch)
+    return eph, tow, np.array(ready, dtype=int)
+
+
+def postNavigate(trackResults, settings):
+    """``NavigationResult.postNavigate`` (postNavigation.py:75-301) on the B200 stages: preamble search and bit
+    summation (``sgx_find_preambles``), ephemeris decoding (host bit slicing), measurement loop
+    (``sgx_nav_solve``).  Returns ``(navSolutions, eph)`` -- ``(None, None)`` with the reference's messages when
+    the record is too short or fewer than four satellites have an ephemeris.  ``navSolutions`` is the recarray of
+    :func:`navSolutions` (no UTM fields); ``eph`` a list of 32 dicts/None indexed by PRN-1."""
+    tracked = (trackResults.status != '-') if trackResults.status.dtype.kind != 'S' else (trackResults.status != b'-')
+    if settings.msToProcess < 36000 or int(tracked.sum()) < 4:                                # :104-111
+        print('Record is to short or too few satellites tracked. Exiting!')
+        return None, None
+    subFrameStart, activeChnList, bits, valid = findPreambles(trackResults, settings, return_bits=True)   # :115
+    prn = [int(trackResults[c].PRN) for c in range(len(trackResults))]
+    eph, TOW, ready = _decode_channels(bits, valid, subFrameStart, prn, activeChnList) if bits is not None \
+        else ([None] * 32, None, np.zeros(0, dtype=int))
+    if ready.size < 4:                                                                        # :149-156
+        print('Too few satellites with ephemeris data for position calculations. Exiting!')
+        return None, None
+    nav, _ = navSolutions(trackResults, subFrameStart, ready, eph, TOW, settings)
+    return nav, eph
+
+
+def post_navigate_batch(track_out, prn, settings, stream=0):
+    """The same chain for R recordings whose tracking result ``track_out`` (float64 ``[R, C, 13, ms]``, numpy or
+    CUDA tensor as written by ``track_batch``) stays where it is: ``I_P`` and ``absoluteSample`` are read in
+    place by the two device stages; only the 1501 hard bits per channel and the solutions cross to the host.
+    ``prn``: int ``[R, C]`` (0 = channel not tracked).  Returns the dict of :func:`nav_solve_batch` plus
+    ``subFrameStart`` ``[R, C]``, ``ready`` ``[R, C]``, ``tow`` ``[R]`` and ``eph`` (R lists indexed by PRN-1);
+    recordings with fewer than four usable satellites get ``n_epochs = 0``."""
+    r, c, nf, ms = track_out.shape
+    prn = np.asarray(prn).reshape(r, c)
+    if isinstance(track_out, np.ndarray):
+        ip = np.ascontiguousarray(track_out[:, :, 3, :]).reshape(r * c, ms)
+        first, bits, valid = find_preambles_batch(ip, stream=stream)
+        abs_in, stride = np.ascontiguousarray(track_out[:, :, 0, :]), ms
+    else:
+        ip = track_out.view(r * c, nf * ms)[:, 3 * ms:4 * ms]              # I_P rows, row stride 13 * ms
+        first, bits, valid = find_preambles_batch(ip, stream=stream)
+        abs_in, stride = track_out, nf * ms
+    first = first.reshape(r, c)
+    first[prn == 0] = 0
+    ready = np.zeros((r, c), dtype=np.uint8)
+    rows = np.zeros((r, c, len(_native.EPH_FIELDS)))
+    tow = np.zeros(r)
+    ephs = []
+    n_ep = np.zeros(r, dtype=np.int32)
+    for i in range(r):
+        cand = [ch for ch in range(c) if prn[i, ch] > 0 and first[i, ch] > 0]
+        eph, t, rdy = _decode_channels(bits[i * c:(i + 1) * c], valid[i * c:(i + 1) * c], first[i], prn[i], cand)
+        ephs.append(eph)
+        if rdy.size >= 4 and settings.msToProcess >= 36000:
+            ready[i, rdy] = 1
+            rows[i] = eph_rows(eph, np.where(ready[i] > 0, prn[i], 0))
+            tow[i] = t
+            n_ep[i] = nav_epochs(settings, first[i])
+    out = _native.lib().nav_solve(abs_in, stride, r, c, ms, first, ready, rows, tow, n_ep, nav_settings(settings),
+                                  stream=stream)
+    out.update(subFrameStart=first, ready=ready, tow=tow, eph=ephs)
+    return out
 
 
 def install(navigation_result_cls):

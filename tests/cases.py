@@ -210,3 +210,56 @@ def build_ephemeris_cases():
                 b[base + 49 + j] = bit ^ inv
         rows.append(b)
     return np.stack(rows)
+
+
+# ---------------------------------------------------------------------------------------------
+# Whole downstream chain (preamble search -> ephemeris decoding -> measurement loop) on a synthetic tracking
+# result: I_P carries the LNAV stream of each satellite, absoluteSample the geometry of navsynth.build_scenario.
+# ---------------------------------------------------------------------------------------------
+def build_chain_case(seed=2, ms=NAV_MS, n_code=38192, fs=38.192e6, first_boundary_ms=5200, drop=()):
+    """Returns (track float64 [C, 13, ms], prn int64 [C], truth).  Channels in ``drop`` carry noise only."""
+    from softgnss_python_b200 import navsynth
+    _, truth = navsynth.build_scenario(seed=seed)
+    n_ch = len(truth["prn"])
+    track = np.zeros((n_ch, 13, ms))
+    rho_min = min(truth["range"])
+    k = np.arange(ms, dtype=np.float64)
+    for c in range(n_ch):
+        e = truth["eph"][c]
+        q = navsynth.quantize_ephemeris(dict(e, weekNumber=2100, IODE=40 + c))
+        sid = 1 + (c % 5)                                                     # subframe that starts at `tow`
+        bits01 = navsynth.encode_stream(q, (sid - 2) % 5 + 1, truth["tow"] - 6, 8)
+        k0 = first_boundary_ms + (3 * c) % 7                                  # index of that boundary in the series
+        per_ms = np.repeat(bits01.astype(np.float64) * 2 - 1, 20)            # stream starts one subframe (6000 ms) earlier
+        idx = np.arange(ms) - k0 + 6000
+        ip = np.where((idx >= 0) & (idx < per_ms.size), per_ms[np.clip(idx, 0, per_ms.size - 1)], 1.0)
+        noise = _hash_noise(seed * 100 + c, ms) * 2.0
+        track[c, 3] = (0.0 if c in drop else 3000.0) * ip * (1 if c % 2 else -1) + noise + 0.25
+        s = []
+        for kk in (0.0, 18000.0, 36000.0):
+            rho, _ = navsynth.geometric_range(e, truth["tow"] + kk * 1e-3, truth["rx"])
+            s.append((rho - rho_min) / navsynth.C * fs)
+        p2 = ((s[2] - s[0]) - 2 * (s[1] - s[0])) / (2 * 18000.0 ** 2)
+        p1 = (s[1] - s[0]) / 18000.0 - p2 * 18000.0
+        kr = k - k0
+        track[c, 0] = np.round(first_boundary_ms * n_code + s[0] + kr * n_code + p1 * kr + p2 * kr * kr)
+    return track, np.array(truth["prn"], dtype=np.int64), truth
+
+
+def oracle_chain(track, prn, settings_kw):
+    """The same chain with the oracle: find_preambles, nav_bits, ephemeris, nav_solve.  Returns (first, nav dict | None)."""
+    from oracle import gnss_oracle as orc
+    n_ch, _, ms = track.shape
+    first, active = orc.find_preambles([track[c, 3] for c in range(n_ch)])
+    eph, tow, ready = [None] * 32, None, []
+    for ch in active:
+        if first[ch] + 30000 > ms:
+            continue
+        b = orc.nav_bits(track[ch, 3], int(first[ch]))
+        e, tow = orc.ephemeris(b[1:], b[0])
+        eph[int(prn[ch]) - 1] = e
+        if e["IODC"] is not None and e["IODE_sf2"] is not None and e["IODE_sf3"] is not None:
+            ready.append(ch)
+    if len(ready) < 4:
+        return first, None
+    return first, orc.nav_solve([track[c, 0] for c in range(n_ch)], prn, first, ready, eph, tow, float(ms), 38192, **settings_kw)

@@ -101,3 +101,53 @@ def test_nav_solve_argument_errors():
     with pytest.raises(_native.NativeError):
         _native.lib().nav_solve(np.zeros((1, 33, 10)), 10, 1, 33, 10, np.zeros((1, 33)), np.zeros((1, 33)),
                                 np.zeros((1, 33, 21)), [0.0], [1], postnav.nav_settings(s))
+
+
+def test_post_navigate_chain_matches_oracle_chain():
+    """Preamble search -> ephemeris decoding -> measurement loop (postnav.post_navigate_batch) on synthetic tracking
+    results (LNAV streams in I_P, geometry in absoluteSample), host and device resident, against the oracle's chain;
+    the fix is the scenario's antenna."""
+    import torch
+    from softgnss_python_b200 import postnav
+    from softgnss_python_b200.settings import Settings
+    from tests.cases import build_chain_case, oracle_chain
+    tr0, prn0, truth0 = build_chain_case(seed=2)
+    tr1, prn1, truth1 = build_chain_case(seed=5, drop=(1, 4, 6, 7, 2))       # three satellites left: no solution
+    tr2, prn2, truth2 = build_chain_case(seed=7, drop=(3,))
+    s = Settings(numberOfChannels=8, msToProcess=float(NAV_MS))
+    kw = dict(elevation_mask=s.elevationMask, use_trop_corr=s.useTropCorr)
+    track = np.stack([tr0, tr1, tr2])
+    prn = np.stack([prn0, prn1, prn2])
+    out = postnav.post_navigate_batch(track, prn, s)
+    dev = postnav.post_navigate_batch(torch.from_numpy(track).cuda(), prn, s)
+    for k in ("sol", "rawP", "el", "active", "subFrameStart", "ready", "n_epochs"):
+        assert np.array_equal(out[k], dev[k], equal_nan=True), k              # device-resident input: same result
+    for r, (tr, p, truth) in enumerate(((tr0, prn0, truth0), (tr1, prn1, truth1), (tr2, prn2, truth2))):
+        first, o = oracle_chain(tr, p, kw)
+        assert np.array_equal(out["subFrameStart"][r], first)
+        if o is None:
+            assert out["n_epochs"][r] == 0
+            continue
+        nav_util.compare_nav(out, r, o, "chain %d" % r)
+        sol = out["sol"][r, :out["n_epochs"][r]]
+        err = np.sqrt(((sol[:, :3] - truth["rx"]) ** 2).sum(1))
+        assert np.isfinite(err).all() and np.median(err) < 30.0, np.median(err)
+    assert out["n_epochs"].tolist() == [63, 0, 63]
+
+
+def test_postNavigate_reference_surface(capsys):
+    from softgnss_python_b200 import postnav
+    from softgnss_python_b200.settings import Settings
+    from tests.cases import build_chain_case
+    tr, prn, truth = build_chain_case(seed=2)
+    s = Settings(numberOfChannels=8, msToProcess=float(NAV_MS))
+    dtype = [('status', 'U1')] + [(f, 'object') for f in orc.TRACK_FIELDS] + [('PRN', 'int64')]
+    res = np.rec.fromrecords([('T',) + tuple(tr[c, i] for i in range(13)) + (int(prn[c]),) for c in range(8)], dtype=dtype)
+    nav, eph = postnav.postNavigate(res, s)
+    assert nav[0].X.shape == (63,) and np.isfinite(nav[0].X).all()
+    err = np.sqrt((nav[0].X - truth["rx"][0]) ** 2 + (nav[0].Y - truth["rx"][1]) ** 2 + (nav[0].Z - truth["rx"][2]) ** 2)
+    assert np.median(err) < 30.0
+    assert abs(eph[int(prn[0]) - 1]["sqrtA"] - truth["eph"][0]["sqrtA"]) < 1e-9
+    s2 = Settings(numberOfChannels=8, msToProcess=20000.0)
+    assert postnav.postNavigate(res, s2) == (None, None)                       # postNavigation.py:104-111
+    assert "Record is to short" in capsys.readouterr().out
