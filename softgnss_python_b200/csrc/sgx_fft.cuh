@@ -117,7 +117,7 @@ constexpr int ROWS_PER_ITER = FFT_THREADS / TILE;
 
 // One Stockham sub-pass of radix r over the R x TILE tile held in shared memory.
 template <int r, bool INV>
-__device__ __forceinline__ void subpass(const cpx* in, cpx* out,   // may alias: the last sub-pass is in place
+__device__ __forceinline__ void subpass(const cpx* __restrict__ in, cpx* __restrict__ out,
                                         const cpx* __restrict__ W, int R, int ls) {
   const int mm = R / r;
   const int total = mm * TILE;
@@ -320,13 +320,8 @@ __global__ void __launch_bounds__(FFT_THREADS) fft_pass_async_kernel(Pass P, Src
     if (INV) w.y = -w.y;
     W[q] = w;
   }
-  // Software pipeline: the last Stockham sub-pass writes every butterfly back to the positions it read
-  // (ls == R / r), so with at most two sub-passes the work stays in A and the staging tiles S1 / S2 are free as
-  // soon as the first sub-pass has consumed them -- the next transform's cp.async is issued there and overlaps
-  // with the second sub-pass and the epilogue.
-  const bool pipelined = P.nsub <= 2;
   const cpx* aux_cached = nullptr;
-  auto stage = [&](int batch) {
+  for (int batch = b_begin; batch < b_end; ++batch) {
     const cpx* src;
     const cpx* aux;
     srcd.locate(batch, src, aux);
@@ -343,28 +338,20 @@ __global__ void __launch_bounds__(FFT_THREADS) fft_pass_async_kernel(Pass P, Src
     for (int t = t0; t < R; t += ROWS_PER_ITER)
       if (valid) cp_async8(&S1[t * TILE + jj], src + (size_t)t * m + j);
     cp_async_commit();
-  };
-  if (b_begin < b_end) stage(b_begin);
-  for (int batch = b_begin; batch < b_end; ++batch) {
     cp_async_wait_all();
-    __syncthreads();   // staged tiles visible; every thread has left the previous epilogue (A may be rewritten)
+    __syncthreads();
     // first sub-pass: staged operands -> A
     run_subpass_first<INV, BIG, AUX>(P.radix[0], S1, S2, A, R);
     __syncthreads();
-    if (pipelined && batch + 1 < b_end) stage(batch + 1);
     cpx* cur = A;
     cpx* oth = S1;
     int ls = P.radix[0];
     for (int s = 1; s < P.nsub; ++s) {
       const int r = P.radix[s];
-      if (pipelined) {
-        run_subpass<INV, BIG>(r, cur, cur, W, R, ls);   // last sub-pass: in place
-      } else {
-        run_subpass<INV, BIG>(r, cur, oth, W, R, ls);
-        cpx* tmp = cur; cur = oth; oth = tmp;
-      }
+      run_subpass<INV, BIG>(r, cur, oth, W, R, ls);
       ls *= r;
       __syncthreads();
+      cpx* tmp = cur; cur = oth; oth = tmp;
     }
     epi.begin(batch);
     if (Ls == 1) {
@@ -378,10 +365,7 @@ __global__ void __launch_bounds__(FFT_THREADS) fft_pass_async_kernel(Pass P, Src
       for (int u = t0; u < R; u += ROWS_PER_ITER) epi.put(base + u * Ls, cur[u * TILE_P + jj]);
     }
     epi.finish(batch, tile);
-    if (!pipelined) {
-      __syncthreads();   // S1 / A are overwritten by the next transform
-      if (batch + 1 < b_end) stage(batch + 1);
-    }
+    __syncthreads();   // S1 / A are overwritten by the next transform
   }
 }
 
