@@ -349,9 +349,23 @@ static int launch_pass_async(const fft::Plan& pl, int p, bool inverse, int batch
     SGX_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_async[p])); \
     SGX_COUNTED_LAUNCH(kfn, grid, dim3(fft::FFT_THREADS), pl.smem_async[p], s, P, src, epi, batch, ipc);  \
   }
-  if (inverse) { if (pl.big) SGX_FFT_GO(true, true) else SGX_FFT_GO(true, false) }
+#define SGX_FFT_GO2(INV, BIG, R0, R1)                                                                     \
+  {                                                                                                       \
+    auto kfn = fft::fft_pass_async_kernel<Src, Epi, INV, BIG, AUX, R0, R1>;                               \
+    SGX_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_async[p])); \
+    SGX_COUNTED_LAUNCH(kfn, grid, dim3(fft::FFT_THREADS), pl.smem_async[p], s, P, src, epi, batch, ipc);  \
+  }
+  // compile-time radices for the hot shapes (SGX_FFT_GENERIC=1 forces the generic kernel; used by the tests)
+  static const bool generic_only = getenv("SGX_FFT_GENERIC") && getenv("SGX_FFT_GENERIC")[0] == '1';
+  const int r0 = P.radix[0], r1 = P.nsub == 2 ? P.radix[1] : 0;
+  if (!generic_only && P.nsub == 2 && inverse && pl.big && r0 == 31 && r1 == 7) SGX_FFT_GO2(true, true, 31, 7)
+  else if (!generic_only && P.nsub == 2 && inverse && pl.big && r0 == 16 && r1 == 11) SGX_FFT_GO2(true, true, 16, 11)
+  else if (!generic_only && P.nsub == 2 && !inverse && !pl.big && r0 == 16 && r1 == 16) SGX_FFT_GO2(false, false, 16, 16)
+  else if (!generic_only && P.nsub == 2 && !inverse && !pl.big && r0 == 16 && r1 == 8) SGX_FFT_GO2(false, false, 16, 8)
+  else if (inverse) { if (pl.big) SGX_FFT_GO(true, true) else SGX_FFT_GO(true, false) }
   else         { if (pl.big) SGX_FFT_GO(false, true) else SGX_FFT_GO(false, false) }
 #undef SGX_FFT_GO
+#undef SGX_FFT_GO2
   SGX_CUDA(cudaGetLastError());
   return SGX_OK;
 }

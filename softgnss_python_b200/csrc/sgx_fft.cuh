@@ -294,11 +294,16 @@ __device__ __forceinline__ void run_subpass_first(int r, const cpx* s1, const cp
   }
 }
 
-template <class Src, class Epi, bool INV, bool BIG, int AUX>
+// R0, R1 != 0: the pass is exactly two sub-passes of radices R0 and R1 known at compile time (the hot shapes
+// 217 = 31 x 7, 176 = 16 x 11 of the 38192-point search and 256 = 16 x 16, 128 = 16 x 8 of the fine search), so
+// every loop over rows has a constant trip count and the shared-memory index arithmetic folds into immediates --
+// profiles/ncu_summary_r1_v4.md: the generic kernel spends ~40 % of its instructions on integer/branch work.
+template <class Src, class Epi, bool INV, bool BIG, int AUX, int R0 = 0, int R1 = 0>
 __global__ void __launch_bounds__(FFT_THREADS) fft_pass_async_kernel(Pass P, Src srcd, Epi epi, int n_batch,
                                                                       int items_per_cta) {
   SGX_DYN_SMEM(smem);
-  const int R = P.R, m = P.m, Ls = P.Ls;
+  const int R = R0 ? R0 * R1 : P.R;
+  const int m = P.m, Ls = P.Ls;
   cpx* S1 = reinterpret_cast<cpx*>(smem);          // staged operand [R][16]; later a padded work buffer
   cpx* A = S1 + R * TILE_P;                        // padded work buffer [R][17]
   cpx* S2 = A + R * TILE_P;                        // second operand tile [R][16]
@@ -341,17 +346,26 @@ __global__ void __launch_bounds__(FFT_THREADS) fft_pass_async_kernel(Pass P, Src
     cp_async_wait_all();
     __syncthreads();
     // first sub-pass: staged operands -> A
-    run_subpass_first<INV, BIG, AUX>(P.radix[0], S1, S2, A, R);
-    __syncthreads();
     cpx* cur = A;
     cpx* oth = S1;
-    int ls = P.radix[0];
-    for (int s = 1; s < P.nsub; ++s) {
-      const int r = P.radix[s];
-      run_subpass<INV, BIG>(r, cur, oth, W, R, ls);
-      ls *= r;
+    if (R0) {
+      subpass_first<(R0 ? R0 : 2), INV, AUX>(S1, S2, A, R);
       __syncthreads();
-      cpx* tmp = cur; cur = oth; oth = tmp;
+      subpass<(R1 ? R1 : 2), INV>(A, S1, W, R, R0);
+      __syncthreads();
+      cur = S1;
+      oth = A;
+    } else {
+      run_subpass_first<INV, BIG, AUX>(P.radix[0], S1, S2, A, R);
+      __syncthreads();
+      int ls = P.radix[0];
+      for (int s = 1; s < P.nsub; ++s) {
+        const int r = P.radix[s];
+        run_subpass<INV, BIG>(r, cur, oth, W, R, ls);
+        ls *= r;
+        __syncthreads();
+        cpx* tmp = cur; cur = oth; oth = tmp;
+      }
     }
     epi.begin(batch);
     if (Ls == 1) {
