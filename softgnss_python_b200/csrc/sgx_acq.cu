@@ -129,7 +129,14 @@ struct FineItem {
   int rec, prn, codePhase, pad;
 };
 
-struct ProFine {  // A10: (x - mean) * code, zero padded
+// A10: (x - mean) * code, zero padded.  The reference's transform has nfft = 8 * 2^ceil(log2(nvalid)) points of which
+// at most nfft/8 are non-zero, so the first radix-8 decimation-in-frequency stage is trivial:
+//     X[8 k' + s] = sum_{n < nfft/8} (x[n] * w_nfft^(n s)) * w_{nfft/8}^(n k'),
+// i.e. eight independent transforms of nfft/8 points of the input times a phase ramp.  The input is real, so
+// X[nfft - k] = conj(X[k]) and the ramps s = 5, 6, 7 are the mirrored upper halves of s = 3, 2, 1: five
+// sub-transforms (s = 0..4) give |X[k]| for every k < nfft/2 (see EpiFine).  batch = item * FINE_SUBS + s.
+constexpr int FINE_SUBS = 5;
+struct ProFine {
   const int8_t* sig;
   long long rec_stride;
   const long long* sums;  // [rec] integer sum of the whole recording
@@ -137,17 +144,25 @@ struct ProFine {  // A10: (x - mean) * code, zero padded
   const int8_t* chips;        // [32][1023]
   const unsigned short* idx;  // [nvalid]
   const FineItem* items;
-  int nvalid;
+  int nvalid, nfft;
   float mean;
+  int sub;
   __device__ __forceinline__ void prepare(int batch) {
-    const FineItem it = items[batch];
+    const FineItem it = items[batch / FINE_SUBS];
+    sub = batch % FINE_SUBS;
     mean = (float)((double)sums[it.rec] / (double)n_samples);
     sig += (long long)it.rec * rec_stride + it.codePhase;
     chips += it.prn * 1023;
   }
   __device__ __forceinline__ cpx load(int i) const {
     if (i >= nvalid) return make_float2(0.f, 0.f);
-    return make_float2(((float)sig[i] - mean) * (float)chips[idx[i]], 0.f);
+    const float x = ((float)sig[i] - mean) * (float)chips[idx[i]];
+    if (sub == 0) return make_float2(x, 0.f);
+    // w_nfft^(i*sub): the phase fraction (i*sub mod nfft) / nfft is exact in float32 (nfft <= 2^24)
+    const unsigned q = ((unsigned)i * (unsigned)sub) & (unsigned)(nfft - 1);
+    float sn, cs;
+    sincospif(-2.0f * ((float)q / (float)nfft), &sn, &cs);
+    return make_float2(x * cs, x * sn);
   }
 };
 
@@ -201,12 +216,23 @@ struct EpiSecond {  // arg-max over the candidates only
   }
 };
 
-struct EpiFine {  // acquisition.py:186-187: arg-max over fftxc[4 : uniq-5], index relative to the slice
+// acquisition.py:186-187: arg-max over fftxc[4 : uniq-5], index relative to the slice.  Output kp of sub-transform
+// s is bin 8 kp + s of the reference's spectrum; for s = 1, 2, 3 its upper half is, mirrored, bin
+// nfft - (8 kp + s) = 8 (msub - 1 - kp) + (8 - s) (same magnitude, real input).  Every bin below nfft/2 occurs once.
+struct EpiFine {
   unsigned long long* partial;
   int ntiles, lo, hi;  // candidates lo <= k < hi
+  int msub;            // points of a sub-transform (nfft / 8)
   unsigned long long best;
-  __device__ __forceinline__ void begin(int) { best = 0ull; }
-  __device__ __forceinline__ void put(int i, cpx v) {
+  int sub;
+  __device__ __forceinline__ void begin(int batch) { best = 0ull; sub = batch % FINE_SUBS; }
+  __device__ __forceinline__ void put(int kp, cpx v) {
+    int i;
+    if (kp < (msub >> 1)) i = 8 * kp + sub;
+    else {
+      if (sub == 0 || sub == 4) return;
+      i = 8 * (msub - 1 - kp) + (8 - sub);
+    }
     if (i < lo || i >= hi) return;
     const float mag = fmaf(v.x, v.x, v.y * v.y);
     const unsigned long long k = fft::peak_key(mag, (unsigned)(i - lo));
@@ -463,7 +489,7 @@ static int ensure_plan(const sgx_settings* st, const int8_t* ca_table, const int
   int rc;
   if ((rc = fft::build_plan(a.fwd, a.n, false, s))) return rc;
   if ((rc = fft::build_plan(a.inv, a.n, true, s))) return rc;
-  if ((rc = fft::build_plan(a.fine, a.nfft, false, s))) return rc;
+  if ((rc = fft::build_plan(a.fine, a.nfft / 8, false, s))) return rc;   // sub-transforms, see ProFine
   if (a.table.reserve((size_t)32 * n1) || a.chips.reserve(32 * 1023) || a.fidx.reserve(sizeof(uint16_t) * a.nvalid) ||
       a.codeF.reserve(sizeof(cpx) * (size_t)32 * a.n) || a.cps.reserve(sizeof(double) * st->numFrqBins) ||
       a.work0.reserve(sizeof(cpx) * (size_t)32 * a.n) || a.work1.reserve(sizeof(cpx) * (size_t)32 * a.n))
@@ -530,7 +556,7 @@ extern "C" int sgx_acquire(const int8_t* sig, int64_t rec_stride, int64_t n_samp
   const int npr = R * prn_count;
   const int nt_last = a.inv.pass[a.inv.npass - 1].ntiles;
   // scratch
-  long long chunk_mb = 256;
+  long long chunk_mb = 512;   // measured on B200 (32-recording batch): 256 MB 38.8 ms, 512 MB 38.0 ms, 1024 MB 40.6 ms
   if (const char* e = getenv("SGX_ACQ_CHUNK_MB")) chunk_mb = atoll(e) > 0 ? atoll(e) : chunk_mb;
   long long chunk = (chunk_mb << 20) / ((long long)sizeof(cpx) * n);
   if (chunk < 1) chunk = 1;
@@ -624,31 +650,39 @@ extern "C" int sgx_acquire(const int8_t* sig, int64_t rec_stride, int64_t n_samp
   if (nf > 0) {
     const int nt_f = a.fine.pass[a.fine.npass - 1].ntiles;
     const int uniq = a.nfft / 2 + 1;                                      // ceil((nfft+1)/2), :184
-    int fchunk = (int)((256LL << 20) / ((long long)sizeof(cpx) * a.nfft));
+    const int msub = a.nfft / 8;
+    // items per chunk.  Measured on B200 (212 detected PRNs): 16-48 MB (L2-resident ping-pong buffers) 42-43.7 ms
+    // per batch, 96 MB 41.2, 256 MB 39.4, 512 MB 38.8, 1024 MB 38.6: fewer, larger launches win over L2 residency.
+    long long fine_mb = 512;
+    if (const char* e = getenv("SGX_ACQ_FINE_CHUNK_MB")) fine_mb = atoll(e) > 0 ? atoll(e) : fine_mb;
+    int fchunk = (int)((fine_mb << 20) / ((long long)sizeof(cpx) * msub * FINE_SUBS));
     if (fchunk < 1) fchunk = 1;
-    if (a.fitems.reserve(sizeof(FineItem) * nf) || a.fpartial.reserve(sizeof(unsigned long long) * (size_t)nf * nt_f) ||
-        a.findex.reserve(sizeof(int) * nf) || a.work0.reserve(sizeof(cpx) * (size_t)fchunk * a.nfft) ||
-        a.work1.reserve(sizeof(cpx) * (size_t)fchunk * a.nfft))
+    if (fchunk > 65535 / FINE_SUBS) fchunk = 65535 / FINE_SUBS;
+    const size_t wfine = sizeof(cpx) * (size_t)fchunk * FINE_SUBS * msub;
+    if (a.fitems.reserve(sizeof(FineItem) * nf) ||
+        a.fpartial.reserve(sizeof(unsigned long long) * (size_t)nf * FINE_SUBS * nt_f) ||
+        a.findex.reserve(sizeof(int) * nf) || a.work0.reserve(wfine) || a.work1.reserve(wfine))
       return fail(SGX_ERR_CUDA, "cudaMalloc", "fine search scratch");
     SGX_CUDA(cudaMemcpyAsync(a.fitems.p, items, sizeof(FineItem) * nf, cudaMemcpyHostToDevice, s));
     for (int f0 = 0; f0 < nf; f0 += fchunk) {
       const int cnt = nf - f0 < fchunk ? nf - f0 : fchunk;
       EpiFine ef;
-      ef.partial = a.fpartial.as<unsigned long long>() + (size_t)f0 * nt_f; ef.ntiles = nt_f; ef.lo = 4;
-      ef.hi = uniq - 5; ef.best = 0;
+      ef.partial = a.fpartial.as<unsigned long long>() + (size_t)f0 * FINE_SUBS * nt_f; ef.ntiles = nt_f; ef.lo = 4;
+      ef.hi = uniq - 5; ef.msub = msub; ef.best = 0; ef.sub = 0;
       ProFine pf{d_sig, stride, (const long long*)a.sums.p, (long long)n_samples, a.chips.as<int8_t>(),
-                 a.fidx.as<unsigned short>(), a.fitems.as<FineItem>() + f0, a.nvalid, 0.f};
+                 a.fidx.as<unsigned short>(), a.fitems.as<FineItem>() + f0, a.nvalid, a.nfft, 0.f, 0};
       if (async && a.fine.npass >= 2) {
         // pass 0 (int8 prologue) stays synchronous; the remaining passes stream through the async kernel
-        rc = launch_pass(a.fine, 0, false, cnt, pf, fft::StoreCpx{a.work0.as<cpx>(), (long long)a.nfft, 1.f, 0, nullptr}, s);
-        if (!rc) rc = run_fft_tail_async(a.fine, false, cnt, a.work0.as<cpx>(), a.work1.as<cpx>(), ef, s);
+        rc = launch_pass(a.fine, 0, false, cnt * FINE_SUBS, pf,
+                         fft::StoreCpx{a.work0.as<cpx>(), (long long)msub, 1.f, 0, nullptr}, s);
+        if (!rc) rc = run_fft_tail_async(a.fine, false, cnt * FINE_SUBS, a.work0.as<cpx>(), a.work1.as<cpx>(), ef, s);
       } else {
-        rc = run_fft(a.fine, false, cnt, pf, ef, a.work0.as<cpx>(), a.work1.as<cpx>(), s);
+        rc = run_fft(a.fine, false, cnt * FINE_SUBS, pf, ef, a.work0.as<cpx>(), a.work1.as<cpx>(), s);
       }
       if (rc) return rc;
     }
     SGX_COUNTED_LAUNCH(fine_reduce_kernel, dim3(nf), dim3(fft::FFT_THREADS), 0, s, a.fpartial.as<unsigned long long>(),
-                       nt_f, nf, a.findex.as<int>());
+                       nt_f * FINE_SUBS, nf, a.findex.as<int>());
     SGX_CUDA(cudaGetLastError());
     int* h_idx = (int*)malloc(sizeof(int) * nf);
     SGX_CUDA(cudaMemcpyAsync(h_idx, a.findex.p, sizeof(int) * nf, cudaMemcpyDeviceToHost, s));
