@@ -378,8 +378,8 @@ static int launch_pass_async(const fft::Plan& pl, int p, bool inverse, int batch
 #define SGX_FFT_GO2(INV, BIG, R0, R1)                                                                     \
   {                                                                                                       \
     auto kfn = fft::fft_pass_async_kernel<Src, Epi, INV, BIG, AUX, R0, R1>;                               \
-    SGX_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_async[p])); \
-    SGX_COUNTED_LAUNCH(kfn, grid, dim3(fft::FFT_THREADS), pl.smem_async[p], s, P, src, epi, batch, ipc);  \
+    SGX_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_direct[p])); \
+    SGX_COUNTED_LAUNCH(kfn, grid, dim3(fft::FFT_THREADS), pl.smem_direct[p], s, P, src, epi, batch, ipc);  \
   }
   // compile-time radices for the hot shapes (SGX_FFT_GENERIC=1 forces the generic kernel; used by the tests)
   static const bool generic_only = getenv("SGX_FFT_GENERIC") && getenv("SGX_FFT_GENERIC")[0] == '1';
@@ -398,7 +398,7 @@ static int launch_pass_async(const fft::Plan& pl, int p, bool inverse, int batch
 
 // items per CTA of the persistent pass kernel: enough CTAs to fill the GPU a few times over
 static int pick_ipc(int batch, int ntiles) {
-  const int target_ctas = 148 * 2 * 3;
+  const int target_ctas = 148 * 12;   // whole waves at 2, 3 and 4 resident CTAs per SM
   int ipc = (int)(((long long)batch * ntiles + target_ctas - 1) / target_ctas);
   if (ipc < 1) ipc = 1;
   if (ipc > 32) ipc = 32;

@@ -140,6 +140,30 @@ __device__ __forceinline__ void subpass(const cpx* __restrict__ in, cpx* __restr
   }
 }
 
+// Last sub-pass of a pass (ls == R / r): base + u*ls == b + u*mm, i.e. every butterfly writes the rows it read.
+template <int r, bool INV>
+__device__ __forceinline__ void subpass_inplace(cpx* buf, const cpx* __restrict__ W, int R, int ls) {
+  const int mm = R / r;
+  const int total = mm * TILE;
+  const int wstride = R / (ls * r);
+  for (int idx = threadIdx.x; idx < total; idx += FFT_THREADS) {
+    const int jj = idx & (TILE - 1);
+    const int b = idx / TILE;
+    const int kk = ls > 1 ? b % ls : 0;
+    cpx v[r];
+#pragma unroll
+    for (int u = 0; u < r; ++u) v[u] = buf[(b + u * mm) * TILE_P + jj];
+    if (ls > 1) {
+#pragma unroll
+      for (int u = 1; u < r; ++u) v[u] = cmulf(v[u], W[u * kk * wstride]);
+    }
+    Dft<r, INV>::run(v);
+    const int base = (b - kk) * r + kk;
+#pragma unroll
+    for (int u = 0; u < r; ++u) buf[(base + u * ls) * TILE_P + jj] = v[u];
+  }
+}
+
 template <bool INV, bool BIG>
 __device__ __forceinline__ void run_subpass(int r, const cpx* in, cpx* out, const cpx* W, int R, int ls) {
   switch (r) {
@@ -294,6 +318,35 @@ __device__ __forceinline__ void run_subpass_first(int r, const cpx* s1, const cp
   }
 }
 
+// First sub-pass of the compile-time-radix kernel: the streamed operand goes from global memory straight into the
+// butterfly's registers (r independent 8-byte loads per thread, the 16 threads of a row read one 128-byte line), is
+// multiplied by the cached second operand and leaves as the sub-pass result in A.  No staging tile, no cp.async.
+template <int r, bool INV, int AUX>
+__device__ __forceinline__ void subpass_first_direct(const cpx* __restrict__ src, size_t row_stride, bool valid,
+                                                     const cpx* __restrict__ s2, cpx* __restrict__ out, int R) {
+  const int mm = R / r;
+  const int total = mm * TILE;
+  for (int idx = threadIdx.x; idx < total; idx += FFT_THREADS) {
+    const int jj = idx & (TILE - 1);
+    const int b = idx / TILE;
+    cpx v[r];
+#pragma unroll
+    for (int u = 0; u < r; ++u) v[u] = valid ? __ldg(src + (size_t)(b + u * mm) * row_stride) : make_float2(0.f, 0.f);
+    if (AUX != AUX_NONE) {
+#pragma unroll
+      for (int u = 0; u < r; ++u) {
+        cpx w = s2[(b + u * mm) * TILE + jj];
+        if (AUX == AUX_TWIDDLE && INV) w.y = -w.y;
+        v[u] = cmulf(v[u], w);
+      }
+    }
+    Dft<r, INV>::run(v);
+    const int base = b * r;   // ls == 1
+#pragma unroll
+    for (int u = 0; u < r; ++u) out[(base + u) * TILE_P + jj] = v[u];
+  }
+}
+
 // R0, R1 != 0: the pass is exactly two sub-passes of radices R0 and R1 known at compile time (the hot shapes
 // 217 = 31 x 7, 176 = 16 x 11 of the 38192-point search and 256 = 16 x 16, 128 = 16 x 8 of the fine search), so
 // every loop over rows has a constant trip count and the shared-memory index arithmetic folds into immediates --
@@ -304,8 +357,10 @@ __global__ void __launch_bounds__(FFT_THREADS) fft_pass_async_kernel(Pass P, Src
   SGX_DYN_SMEM(smem);
   const int R = R0 ? R0 * R1 : P.R;
   const int m = P.m, Ls = P.Ls;
+  // generic: S1 staging / second work buffer, A, S2, W.  Compile-time radices: A, S2, W only (direct loads, the
+  // last sub-pass runs in place) -- smem_direct() bytes, which lets a third (R = 217) / fourth (R = 176) CTA onto the SM.
   cpx* S1 = reinterpret_cast<cpx*>(smem);          // staged operand [R][16]; later a padded work buffer
-  cpx* A = S1 + R * TILE_P;                        // padded work buffer [R][17]
+  cpx* A = R0 ? S1 : S1 + R * TILE_P;              // padded work buffer [R][17]
   cpx* S2 = A + R * TILE_P;                        // second operand tile [R][16]
   cpx* W = S2 + R * TILE;
   const int tid = threadIdx.x;
@@ -340,21 +395,21 @@ __global__ void __launch_bounds__(FFT_THREADS) fft_pass_async_kernel(Pass P, Src
       }
       aux_cached = aux;
     }
-    for (int t = t0; t < R; t += ROWS_PER_ITER)
-      if (valid) cp_async8(&S1[t * TILE + jj], src + (size_t)t * m + j);
+    if (!R0) {
+      for (int t = t0; t < R; t += ROWS_PER_ITER)
+        if (valid) cp_async8(&S1[t * TILE + jj], src + (size_t)t * m + j);
+    }
     cp_async_commit();
     cp_async_wait_all();
-    __syncthreads();
-    // first sub-pass: staged operands -> A
+    __syncthreads();   // second operand (and staged tile) visible; A free (previous epilogue finished)
+    // first sub-pass: operands -> A
     cpx* cur = A;
     cpx* oth = S1;
     if (R0) {
-      subpass_first<(R0 ? R0 : 2), INV, AUX>(S1, S2, A, R);
+      subpass_first_direct<(R0 ? R0 : 2), INV, AUX>(src + j, (size_t)m, valid, S2, A, R);
       __syncthreads();
-      subpass<(R1 ? R1 : 2), INV>(A, S1, W, R, R0);
+      subpass_inplace<(R1 ? R1 : 2), INV>(A, W, R, R0);   // last sub-pass: ls == R / r, every butterfly writes where it read
       __syncthreads();
-      cur = S1;
-      oth = A;
     } else {
       run_subpass_first<INV, BIG, AUX>(P.radix[0], S1, S2, A, R);
       __syncthreads();
@@ -459,6 +514,7 @@ struct Plan {
   DevBuf tw[4], wr[4];
   size_t smem[4];
   size_t smem_async[4];
+  size_t smem_direct[4];
   bool async_ok[4];
 };
 
@@ -547,6 +603,7 @@ inline int build_plan(Plan& pl, int N, bool inverse, cudaStream_t s, int maxR = 
     P.inverse = inverse ? 1 : 0;
     pl.smem[p] = sizeof(cpx) * ((size_t)2 * P.R * TILE_P + P.R);
     pl.smem_async[p] = sizeof(cpx) * ((size_t)2 * P.R * TILE_P + (size_t)P.R * TILE + P.R);
+    pl.smem_direct[p] = sizeof(cpx) * ((size_t)P.R * TILE_P + (size_t)P.R * TILE + P.R);   // compile-time-radix kernel
     pl.async_ok[p] = (Ls == 1) || (Ls % TILE == 0) || (P.m <= Ls);   // twiddle rows of a tile must not wrap
     if (pl.wr[p].reserve(sizeof(cpx) * P.R)) return fail(SGX_ERR_CUDA, "cudaMalloc", "fft tables");
     SGX_COUNTED_LAUNCH(twiddle_kernel, dim3(4), dim3(128), 0, s, pl.wr[p].as<cpx>(), (long long)P.R, 0, (long long)P.R);
