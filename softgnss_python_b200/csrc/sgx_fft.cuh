@@ -321,8 +321,11 @@ __device__ __forceinline__ void run_subpass_first(int r, const cpx* s1, const cp
 // First sub-pass of the compile-time-radix kernel: the streamed operand goes from global memory straight into the
 // butterfly's registers (r independent 8-byte loads per thread, the 16 threads of a row read one 128-byte line), is
 // multiplied by the cached second operand and leaves as the sub-pass result in A.  No staging tile, no cp.async.
-template <int r, bool INV, int AUX>
+// AUXD: the second operand is read from global memory (L2) too; otherwise from the cached tile s2 [R][16].
+__host__ __device__ constexpr bool aux_direct(int r0) { return r0 != 0 && r0 <= 16; }   // 2 x 31 operands do not fit the register file
+template <int r, bool INV, int AUX, bool AUXD>
 __device__ __forceinline__ void subpass_first_direct(const cpx* __restrict__ src, size_t row_stride, bool valid,
+                                                     const cpx* __restrict__ aux, size_t aux_stride,
                                                      const cpx* __restrict__ s2, cpx* __restrict__ out, int R) {
   const int mm = R / r;
   const int total = mm * TILE;
@@ -333,11 +336,17 @@ __device__ __forceinline__ void subpass_first_direct(const cpx* __restrict__ src
 #pragma unroll
     for (int u = 0; u < r; ++u) v[u] = valid ? __ldg(src + (size_t)(b + u * mm) * row_stride) : make_float2(0.f, 0.f);
     if (AUX != AUX_NONE) {
+      // second operand (code spectrum / inter-pass twiddles) from L2 as well: it is shared by all CTAs of the launch
+      cpx w[r];
 #pragma unroll
       for (int u = 0; u < r; ++u) {
-        cpx w = s2[(b + u * mm) * TILE + jj];
-        if (AUX == AUX_TWIDDLE && INV) w.y = -w.y;
-        v[u] = cmulf(v[u], w);
+        if (AUXD) w[u] = valid ? __ldg(aux + (size_t)(b + u * mm) * aux_stride) : make_float2(0.f, 0.f);
+        else w[u] = s2[(b + u * mm) * TILE + jj];
+      }
+#pragma unroll
+      for (int u = 0; u < r; ++u) {
+        if (AUX == AUX_TWIDDLE && INV) w[u].y = -w[u].y;
+        v[u] = cmulf(v[u], w[u]);
       }
     }
     Dft<r, INV>::run(v);
@@ -358,11 +367,12 @@ __global__ void __launch_bounds__(FFT_THREADS) fft_pass_async_kernel(Pass P, Src
   const int R = R0 ? R0 * R1 : P.R;
   const int m = P.m, Ls = P.Ls;
   // generic: S1 staging / second work buffer, A, S2, W.  Compile-time radices: A, S2, W only (direct loads, the
-  // last sub-pass runs in place) -- smem_direct() bytes, which lets a third (R = 217) / fourth (R = 176) CTA onto the SM.
+  // last sub-pass runs in place) -- smem_direct() bytes, which lets a third (R = 217) / fourth (R = 176) CTA onto the SM (more once the second operand is read from L2 too).
   cpx* S1 = reinterpret_cast<cpx*>(smem);          // staged operand [R][16]; later a padded work buffer
   cpx* A = R0 ? S1 : S1 + R * TILE_P;              // padded work buffer [R][17]
-  cpx* S2 = A + R * TILE_P;                        // second operand tile [R][16]
-  cpx* W = S2 + R * TILE;
+  cpx* S2 = A + R * TILE_P;                        // second operand tile [R][16] (generic kernel only)
+  constexpr bool AUXD = aux_direct(R0);
+  cpx* W = AUXD ? S2 : S2 + R * TILE;
   const int tid = threadIdx.x;
   const int tile = blockIdx.x;
   const int j0 = tile * TILE;
@@ -385,7 +395,7 @@ __global__ void __launch_bounds__(FFT_THREADS) fft_pass_async_kernel(Pass P, Src
     const cpx* src;
     const cpx* aux;
     srcd.locate(batch, src, aux);
-    if (AUX != AUX_NONE && aux != aux_cached) {
+    if (!AUXD && AUX != AUX_NONE && aux != aux_cached) {
       if (AUX == AUX_SAME) {
         for (int t = t0; t < R; t += ROWS_PER_ITER)
           if (valid) cp_async8(&S2[t * TILE + jj], aux + (size_t)t * m + j);
@@ -406,7 +416,9 @@ __global__ void __launch_bounds__(FFT_THREADS) fft_pass_async_kernel(Pass P, Src
     cpx* cur = A;
     cpx* oth = S1;
     if (R0) {
-      subpass_first_direct<(R0 ? R0 : 2), INV, AUX>(src + j, (size_t)m, valid, S2, A, R);
+      subpass_first_direct<(R0 ? R0 : 2), INV, AUX, AUXD>(src + j, (size_t)m, valid,
+                                                          AUX == AUX_SAME ? aux + j : aux + k0 + jj,
+                                                          AUX == AUX_SAME ? (size_t)m : (size_t)Ls, S2, A, R);
       __syncthreads();
       subpass_inplace<(R1 ? R1 : 2), INV>(A, W, R, R0);   // last sub-pass: ls == R / r, every butterfly writes where it read
       __syncthreads();
@@ -603,7 +615,8 @@ inline int build_plan(Plan& pl, int N, bool inverse, cudaStream_t s, int maxR = 
     P.inverse = inverse ? 1 : 0;
     pl.smem[p] = sizeof(cpx) * ((size_t)2 * P.R * TILE_P + P.R);
     pl.smem_async[p] = sizeof(cpx) * ((size_t)2 * P.R * TILE_P + (size_t)P.R * TILE + P.R);
-    pl.smem_direct[p] = sizeof(cpx) * ((size_t)P.R * TILE_P + (size_t)P.R * TILE + P.R);   // compile-time-radix kernel
+    // compile-time-radix kernel: work buffer (+ cached second operand when the first radix is 31) + W
+    pl.smem_direct[p] = sizeof(cpx) * ((size_t)P.R * TILE_P + (aux_direct(P.radix[0]) ? 0 : (size_t)P.R * TILE) + P.R);
     pl.async_ok[p] = (Ls == 1) || (Ls % TILE == 0) || (P.m <= Ls);   // twiddle rows of a tile must not wrap
     if (pl.wr[p].reserve(sizeof(cpx) * P.R)) return fail(SGX_ERR_CUDA, "cudaMalloc", "fft tables");
     SGX_COUNTED_LAUNCH(twiddle_kernel, dim3(4), dim3(128), 0, s, pl.wr[p].as<cpx>(), (long long)P.R, 0, (long long)P.R);
