@@ -331,9 +331,21 @@ static int launch_pass(const fft::Plan& pl, int p, bool inverse, int batch, Pro 
     SGX_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem[p])); \
     SGX_COUNTED_LAUNCH(kfn, grid, dim3(fft::FFT_THREADS), pl.smem[p], s, P, pro, epi);            \
   }
-  if (inverse) { if (pl.big) SGX_FFT_GO(true, true) else SGX_FFT_GO(true, false) }
+#define SGX_FFT_GOS(R0, R1)                                                                       \
+  {                                                                                               \
+    auto kfn = fft::fft_pass_kernel<Pro, Epi, false, false, R0, R1>;                              \
+    SGX_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem[p])); \
+    SGX_COUNTED_LAUNCH(kfn, grid, dim3(fft::FFT_THREADS), pl.smem[p], s, P, pro, epi);            \
+  }
+  const bool pow2_fwd = !inverse && !pl.big && P.nsub == 2 && P.radix[0] == 16 &&
+                        !(getenv("SGX_FFT_GENERIC") && getenv("SGX_FFT_GENERIC")[0] == '1');
+  if (pow2_fwd && P.radix[1] == 16) SGX_FFT_GOS(16, 16)
+  else if (pow2_fwd && P.radix[1] == 8) SGX_FFT_GOS(16, 8)
+  else if (pow2_fwd && P.radix[1] == 4) SGX_FFT_GOS(16, 4)
+  else if (inverse) { if (pl.big) SGX_FFT_GO(true, true) else SGX_FFT_GO(true, false) }
   else         { if (pl.big) SGX_FFT_GO(false, true) else SGX_FFT_GO(false, false) }
 #undef SGX_FFT_GO
+#undef SGX_FFT_GOS
   SGX_CUDA(cudaGetLastError());
   return SGX_OK;
 }
@@ -388,6 +400,7 @@ static int launch_pass_async(const fft::Plan& pl, int p, bool inverse, int batch
   else if (!generic_only && P.nsub == 2 && inverse && pl.big && r0 == 16 && r1 == 11) SGX_FFT_GO2(true, true, 16, 11)
   else if (!generic_only && P.nsub == 2 && !inverse && !pl.big && r0 == 16 && r1 == 16) SGX_FFT_GO2(false, false, 16, 16)
   else if (!generic_only && P.nsub == 2 && !inverse && !pl.big && r0 == 16 && r1 == 8) SGX_FFT_GO2(false, false, 16, 8)
+  else if (!generic_only && P.nsub == 2 && !inverse && !pl.big && r0 == 16 && r1 == 4) SGX_FFT_GO2(false, false, 16, 4)
   else if (inverse) { if (pl.big) SGX_FFT_GO(true, true) else SGX_FFT_GO(true, false) }
   else         { if (pl.big) SGX_FFT_GO(false, true) else SGX_FFT_GO(false, false) }
 #undef SGX_FFT_GO

@@ -188,10 +188,11 @@ __device__ __forceinline__ void run_subpass(int r, const cpx* in, cpx* out, cons
 // Epi:  void begin(int batch);    void put(int n, cpx v);    void finish(int batch, int tile)
 // Every thread owns one column (jj = tid % 16) for the whole kernel, so all index arithmetic that
 // depends on the column or on the batch is done once.
-template <class Pro, class Epi, bool INV, bool BIG>
+template <class Pro, class Epi, bool INV, bool BIG, int R0 = 0, int R1 = 0>
 __global__ void __launch_bounds__(FFT_THREADS) fft_pass_kernel(Pass P, Pro pro, Epi epi) {
   SGX_DYN_SMEM(smem);
-  const int R = P.R, m = P.m, Ls = P.Ls;
+  const int R = R0 ? R0 * R1 : P.R;   // R0, R1: compile-time radices of a two-sub-pass shape (see the persistent kernel)
+  const int m = P.m, Ls = P.Ls;
   cpx* A = reinterpret_cast<cpx*>(smem);
   cpx* B = A + R * TILE_P;
   cpx* W = B + R * TILE_P;
@@ -234,13 +235,21 @@ __global__ void __launch_bounds__(FFT_THREADS) fft_pass_kernel(Pass P, Pro pro, 
   __syncthreads();
   cpx* src = A;
   cpx* dst = B;
-  int ls = 1;
-  for (int s = 0; s < P.nsub; ++s) {
-    const int r = P.radix[s];
-    run_subpass<INV, BIG>(r, src, dst, W, R, ls);
-    ls *= r;
+  if (R0) {
+    subpass<(R0 ? R0 : 2), INV>(A, B, W, R, 1);
     __syncthreads();
-    cpx* tmp = src; src = dst; dst = tmp;
+    subpass_inplace<(R1 ? R1 : 2), INV>(B, W, R, R0);
+    __syncthreads();
+    src = B;
+  } else {
+    int ls = 1;
+    for (int s = 0; s < P.nsub; ++s) {
+      const int r = P.radix[s];
+      run_subpass<INV, BIG>(r, src, dst, W, R, ls);
+      ls *= r;
+      __syncthreads();
+      cpx* tmp = src; src = dst; dst = tmp;
+    }
   }
   epi.begin(batch);
   if (Ls == 1) {
@@ -551,6 +560,25 @@ inline bool factor_small(int n, int* radices, int& cnt) {
 // Split the radices of N into `np` passes with the most even products (exhaustive, tiny).
 inline bool plan_passes(int N, int maxR, int groups[4][MAX_SUB], int gcnt[4], int& np) {
   int rad[16], cnt;
+  if (N >= 2 && (N & (N - 1)) == 0) {
+    // power of two: passes of (nearly) equal size, each one or two sub-passes (16 x 2^k) -- the radix list of
+    // factor_small (16, 16, ..., 8) cannot be split evenly (2^19 came out as 256 x 128 x 16, and a 16-point pass
+    // keeps 16 of the 128 threads busy)
+    int e = 0, lim = 0;
+    while ((1 << e) < N) ++e;
+    while ((2 << lim) <= maxR) ++lim;                 // largest exponent of a pass
+    if (lim > 8) lim = 8;                             // two sub-passes of radix <= 16
+    np = (e + lim - 1) / lim;
+    if (np > 4) return false;
+    for (int g = 0; g < np; ++g) {
+      const int x = e / np + (g < e % np ? 1 : 0);    // exponent of this pass
+      gcnt[g] = 0;
+      if (x > 4) { groups[g][gcnt[g]++] = 16; groups[g][gcnt[g]++] = 1 << (x - 4); }
+      else groups[g][gcnt[g]++] = 1 << x;
+      if (x > 8) return false;
+    }
+    return true;
+  }
   if (!factor_small(N, rad, cnt)) return false;
   for (np = 1; np <= 4; ++np) {
     long long best = -1;
