@@ -378,20 +378,49 @@ static int launch_pass_async(const fft::Plan& pl, int p, bool inverse, int batch
                              cudaStream_t s) {
   if (batch <= 0) return SGX_OK;
   const fft::Pass& P = pl.pass[p];
-  const int groups = (batch + ipc - 1) / ipc;
-  if (groups > 65535) return fail(SGX_ERR_ARG, "launch_pass_async", "batch exceeds gridDim.y");
-  dim3 grid(P.ntiles, groups, 1);
+  // Grid sizing: whole waves.  The CTAs of a launch all do the same work (ipc transforms of one tile position), so a
+  // partially filled last wave is pure loss; the number of resident CTAs per SM differs per instantiation (2..5), so it
+  // is queried once per kernel and the items per CTA are chosen such that tiles x groups fills w waves exactly-ish.
+  (void)ipc;
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (n_sm <= 0) n_sm = 148;
+  }
+  int groups = 1, ipc_w = 1;
+  dim3 grid(P.ntiles, 1, 1);
+#define SGX_FFT_SIZE(SMEM)                                                                                \
+  {                                                                                                       \
+    static int occ = 0;                                                                                   \
+    if (!occ) {                                                                                           \
+      SGX_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM)));      \
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, fft::FFT_THREADS, (SMEM)) != cudaSuccess || occ < 1) occ = 2; \
+    }                                                                                                     \
+    const long long slots = (long long)n_sm * occ, total = (long long)batch * P.ntiles;                  \
+    long long w = (total + slots * 12 - 1) / (slots * 12);        /* about 12 transforms per CTA */        \
+    if (w < 1) w = 1;                                                                                     \
+    long long g = slots * w / P.ntiles;                                                                   \
+    if (g < 1) g = 1;                                                                                     \
+    if (g > 65535) g = 65535;                                                                             \
+    ipc_w = (int)((batch + g - 1) / g);                                                                   \
+    groups = (batch + ipc_w - 1) / ipc_w;                                                                 \
+    grid = dim3(P.ntiles, groups, 1);                                                                     \
+  }
 #define SGX_FFT_GO(INV, BIG)                                                                              \
   {                                                                                                       \
     auto kfn = fft::fft_pass_async_kernel<Src, Epi, INV, BIG, AUX>;                                       \
+    SGX_FFT_SIZE(pl.smem_async[p])                                                                        \
     SGX_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_async[p])); \
-    SGX_COUNTED_LAUNCH(kfn, grid, dim3(fft::FFT_THREADS), pl.smem_async[p], s, P, src, epi, batch, ipc);  \
+    SGX_COUNTED_LAUNCH(kfn, grid, dim3(fft::FFT_THREADS), pl.smem_async[p], s, P, src, epi, batch, ipc_w);  \
   }
 #define SGX_FFT_GO2(INV, BIG, R0, R1)                                                                     \
   {                                                                                                       \
     auto kfn = fft::fft_pass_async_kernel<Src, Epi, INV, BIG, AUX, R0, R1>;                               \
+    SGX_FFT_SIZE(pl.smem_direct[p])                                                                       \
     SGX_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_direct[p])); \
-    SGX_COUNTED_LAUNCH(kfn, grid, dim3(fft::FFT_THREADS), pl.smem_direct[p], s, P, src, epi, batch, ipc);  \
+    SGX_COUNTED_LAUNCH(kfn, grid, dim3(fft::FFT_THREADS), pl.smem_direct[p], s, P, src, epi, batch, ipc_w);  \
   }
   // compile-time radices for the hot shapes (SGX_FFT_GENERIC=1 forces the generic kernel; used by the tests)
   static const bool generic_only = getenv("SGX_FFT_GENERIC") && getenv("SGX_FFT_GENERIC")[0] == '1';
@@ -405,6 +434,7 @@ static int launch_pass_async(const fft::Plan& pl, int p, bool inverse, int batch
   else         { if (pl.big) SGX_FFT_GO(false, true) else SGX_FFT_GO(false, false) }
 #undef SGX_FFT_GO
 #undef SGX_FFT_GO2
+#undef SGX_FFT_SIZE
   SGX_CUDA(cudaGetLastError());
   return SGX_OK;
 }
