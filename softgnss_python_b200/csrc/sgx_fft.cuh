@@ -455,7 +455,8 @@ __global__ void __launch_bounds__(FFT_THREADS) fft_pass_async_kernel(Pass P, Src
       for (int u = t0; u < R; u += ROWS_PER_ITER) epi.put(base + u * Ls, cur[u * TILE_P + jj]);
     }
     epi.finish(batch, tile);
-    __syncthreads();   // S1 / A are overwritten by the next transform
+    if (!R0) __syncthreads();   // S1 is refilled by the next transform's cp.async (compile-time radices: the barrier
+                                // at the top of the loop is the only one needed before A is rewritten)
   }
 }
 
