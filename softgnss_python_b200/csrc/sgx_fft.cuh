@@ -370,7 +370,7 @@ __device__ __forceinline__ void subpass_first_direct(const cpx* __restrict__ src
 // every loop over rows has a constant trip count and the shared-memory index arithmetic folds into immediates --
 // profiles/ncu_summary_r1_v4.md: the generic kernel spends ~40 % of its instructions on integer/branch work.
 template <class Src, class Epi, bool INV, bool BIG, int AUX, int R0 = 0, int R1 = 0>
-__global__ void __launch_bounds__(FFT_THREADS) fft_pass_async_kernel(Pass P, Src srcd, Epi epi, int n_batch,
+__global__ void __launch_bounds__(FFT_THREADS, (R0 == 16 ? 6 : 1)) fft_pass_async_kernel(Pass P, Src srcd, Epi epi, int n_batch,
                                                                       int items_per_cta) {
   SGX_DYN_SMEM(smem);
   const int R = R0 ? R0 * R1 : P.R;
