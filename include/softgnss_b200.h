@@ -132,7 +132,8 @@ int sgx_synth_generate(int8_t* out, int64_t rec_stride, int64_t n_samples, int64
                        int32_t n_recordings, const sgx_synth_spec* specs, const int8_t* bits,
                        const int16_t* lut, const int8_t* ca_chips, void* cuda_stream);
 
-/* Test hook: unnormalised complex FFT (inverse != 0: conjugate twiddles) of `batch` rows of length n
+/* Test hook: unnormalised complex FFT (inverse bit 0: conjugate twiddles; bit 1: passes after the first run through
+ * the persistent pass kernels, as in sgx_acquire) of `batch` rows of length n
  * through the acquisition path's FFT engine; host pointers, interleaved float32 re/im.  n must factor
  * over {2,3,5,7,11,31}.  The counterpart of np.fft.fft / n*np.fft.ifft at acquisition.py:95-126,182. */
 int sgx_fft_c2c(const float* in, float* out, int32_t n, int32_t batch, int32_t inverse, void* cuda_stream);

@@ -113,14 +113,15 @@ class Lib(object):
                                 ctypes.c_void_p(stream))
         return rc, ms_done
 
-    def fft(self, x, inverse=False, stream=0):
-        """Unnormalised FFT of the rows of complex64 x through the acquisition FFT engine (test hook)."""
+    def fft(self, x, inverse=False, stream=0, persistent=False):
+        """Unnormalised FFT of the rows of complex64 x through the acquisition FFT engine (test hook);
+        ``persistent``: passes after the first use the persistent pass kernels of the search."""
         self.require_device()
         x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.complex64)
         out = np.empty_like(x)
         self.dll.sgx_fft_c2c.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32,
                                          ctypes.c_int32, ctypes.c_void_p]
-        self.check(self.dll.sgx_fft_c2c(_ptr(x), _ptr(out), x.shape[1], x.shape[0], int(bool(inverse)),
+        self.check(self.dll.sgx_fft_c2c(_ptr(x), _ptr(out), x.shape[1], x.shape[0], int(bool(inverse)) | (2 if persistent else 0),
                                         ctypes.c_void_p(stream)))
         return out
 

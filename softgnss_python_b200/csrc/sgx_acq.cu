@@ -752,15 +752,25 @@ extern "C" int sgx_fft_c2c(const float* in, float* out, int32_t n, int32_t batch
   if (!in || !out || n < 2 || batch < 1) return fail(SGX_ERR_ARG, "sgx_fft_c2c", "bad argument");
   cudaStream_t s = (cudaStream_t)cuda_stream;
   static fft::Plan pl;   // rebuilt on every call: this is a test hook, not a hot path
-  int rc = fft::build_plan(pl, n, inverse != 0, s);
+  int rc = fft::build_plan(pl, n, (inverse & 1) != 0, s);
   if (rc) return rc;
   static DevBuf bin, bout, w0, w1;
   const size_t bytes = sizeof(cpx) * (size_t)n * batch;
   if (bin.reserve(bytes) || bout.reserve(bytes) || w0.reserve(bytes) || w1.reserve(bytes))
     return fail(SGX_ERR_CUDA, "cudaMalloc", "fft test buffers");
   SGX_CUDA(cudaMemcpyAsync(bin.p, in, bytes, cudaMemcpyHostToDevice, s));
-  rc = run_fft(pl, inverse != 0, batch, fft::LoadCpx{bin.as<cpx>(), (long long)n, nullptr},
-               fft::StoreCpx{bout.as<cpx>(), (long long)n, 1.f, 0, nullptr}, w0.as<cpx>(), w1.as<cpx>(), s);
+  const bool inv = (inverse & 1) != 0;
+  bool persistent = (inverse & 2) != 0 && pl.npass >= 2;       // passes 1.. through the persistent kernels, as in sgx_acquire
+  for (int p = 1; p < pl.npass; ++p) persistent = persistent && pl.async_ok[p];
+  if (persistent) {
+    rc = launch_pass(pl, 0, inv, batch, fft::LoadCpx{bin.as<cpx>(), (long long)n, nullptr},
+                     fft::StoreCpx{w0.as<cpx>(), (long long)n, 1.f, 0, nullptr}, s);
+    if (!rc) rc = run_fft_tail_async(pl, inv, batch, w0.as<cpx>(), w1.as<cpx>(),
+                                     fft::StoreCpx{bout.as<cpx>(), (long long)n, 1.f, 0, nullptr}, s);
+  } else {
+    rc = run_fft(pl, inv, batch, fft::LoadCpx{bin.as<cpx>(), (long long)n, nullptr},
+                 fft::StoreCpx{bout.as<cpx>(), (long long)n, 1.f, 0, nullptr}, w0.as<cpx>(), w1.as<cpx>(), s);
+  }
   if (rc) return rc;
   SGX_CUDA(cudaMemcpyAsync(out, bout.p, bytes, cudaMemcpyDeviceToHost, s));
   SGX_CUDA(cudaStreamSynchronize(s));
