@@ -16,6 +16,8 @@
 // epilogue, so correlation rows are never written.  The second peak needs the winning row again:
 // it is recomputed for the one winning (bin, block) per PRN with a masked arg-max epilogue
 // (32 extra inverse FFTs, +1.7 %).  All transforms are float32.
+#include <vector>
+
 #include "sgx_fft.cuh"
 
 namespace sgx {
@@ -541,14 +543,13 @@ static int ensure_plan(const sgx_settings* st, const int8_t* ca_table, const int
   SGX_CUDA(cudaMemcpyAsync(a.chips.p, ca_chips, 32 * 1023, cudaMemcpyHostToDevice, s));
   SGX_CUDA(cudaMemcpyAsync(a.fidx.p, fine_idx, sizeof(uint16_t) * a.nvalid, cudaMemcpyHostToDevice, s));
   // Doppler grid (acquisition.py:99-101) in float64 on the host
-  double* cps = (double*)malloc(sizeof(double) * st->numFrqBins);
+  std::vector<double> cps(st->numFrqBins);   // (RAII: SGX_CUDA returns early on errors)
   for (int k = 0; k < st->numFrqBins; ++k) {
     const double f = st->IF - st->acqSearchBand / 2 * 1000 + st->acqDopplerStep * k;
     cps[k] = f / st->samplingFreq;
   }
-  SGX_CUDA(cudaMemcpyAsync(a.cps.p, cps, sizeof(double) * st->numFrqBins, cudaMemcpyHostToDevice, s));
+  SGX_CUDA(cudaMemcpyAsync(a.cps.p, cps.data(), sizeof(double) * st->numFrqBins, cudaMemcpyHostToDevice, s));
   SGX_CUDA(cudaStreamSynchronize(s));
-  free(cps);
   // A5: conj(FFT(code)) / n for all 32 PRNs
   rc = run_fft(a.fwd, false, 32, ProCode{a.table.as<int8_t>(), n1},
                fft::StoreCpx{a.codeF.as<cpx>(), (long long)a.n, 1.0f / (float)a.n, 1, nullptr}, a.work0.as<cpx>(),
@@ -660,15 +661,18 @@ extern "C" int sgx_acquire(const int8_t* sig, int64_t rec_stride, int64_t n_samp
   SGX_COUNTED_LAUNCH(metric_kernel, dim3((npr + 127) / 128), dim3(128), 0, s, a.partial2.as<unsigned long long>(),
                      nt_last, a.sel.as<PeakSel>(), npr, a.metric.as<double>(), a.cph.as<int>(), a.fbin.as<int>());
   SGX_CUDA(cudaGetLastError());
-  int* h_cph = (int*)malloc(sizeof(int) * npr * 2);
+  std::vector<int> h_cph_v((size_t)npr * 2);   // host staging is RAII: the SGX_CUDA checks below return early on errors
+  int* h_cph = h_cph_v.data();
   int* h_bin = h_cph + npr;
   SGX_CUDA(cudaMemcpyAsync(peakMetric, a.metric.p, sizeof(double) * npr, cudaMemcpyDeviceToHost, s));
   SGX_CUDA(cudaMemcpyAsync(h_cph, a.cph.p, sizeof(int) * npr, cudaMemcpyDeviceToHost, s));
   SGX_CUDA(cudaMemcpyAsync(h_bin, a.fbin.p, sizeof(int) * npr, cudaMemcpyDeviceToHost, s));
   SGX_CUDA(cudaStreamSynchronize(s));
   // ---- decision (acquisition.py:166) and A10 for the detected PRNs ----------------------------
-  FineItem* items = (FineItem*)malloc(sizeof(FineItem) * npr);
-  int* slot = (int*)malloc(sizeof(int) * npr);
+  std::vector<FineItem> items_v(npr);
+  std::vector<int> slot_v(npr);
+  FineItem* items = items_v.data();
+  int* slot = slot_v.data();
   int nf = 0;
   for (int i = 0; i < npr; ++i) {
     carrFreq[i] = 0.0;
@@ -727,7 +731,8 @@ extern "C" int sgx_acquire(const int8_t* sig, int64_t rec_stride, int64_t n_samp
     SGX_COUNTED_LAUNCH(fine_reduce_kernel, dim3(nf), dim3(fft::FFT_THREADS), 0, s, a.fpartial.as<unsigned long long>(),
                        nt_f * FINE_SUBS, nf, a.findex.as<int>());
     SGX_CUDA(cudaGetLastError());
-    int* h_idx = (int*)malloc(sizeof(int) * nf);
+    std::vector<int> h_idx_v(nf);
+    int* h_idx = h_idx_v.data();
     SGX_CUDA(cudaMemcpyAsync(h_idx, a.findex.p, sizeof(int) * nf, cudaMemcpyDeviceToHost, s));
     SGX_CUDA(cudaStreamSynchronize(s));
     for (int f = 0; f < nf; ++f) {
@@ -735,11 +740,7 @@ extern "C" int sgx_acquire(const int8_t* sig, int64_t rec_stride, int64_t n_samp
       carrFreq[slot[f]] = (double)h_idx[f] * st->samplingFreq / (double)a.nfft;
       if (finePeakIndex) finePeakIndex[slot[f]] = h_idx[f];
     }
-    free(h_idx);
   }
-  free(items);
-  free(slot);
-  free(h_cph);
   return SGX_OK;
 }
 

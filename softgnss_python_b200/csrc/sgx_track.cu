@@ -26,6 +26,7 @@
 //    one shared-memory exchange;
 //  * thread 0 then runs T8/T9/T5/T3 in float64 with separately rounded operations (compiled with
 //    -fmad=false) exactly in the reference's order and publishes the next period's parameters.
+#include <vector>
 #include "sgx_common.cuh"
 
 namespace sgx {
@@ -1099,7 +1100,8 @@ extern "C" int sgx_track(const int8_t* rec, int64_t rec_stride, const int64_t* r
   }
   SGX_CUDA(cudaGetLastError());
   if (out_on_host) SGX_CUDA(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, s));
-  int* h_status = (int*)malloc(sizeof(int) * nch);
+  std::vector<int> h_status_v(nch);   // RAII: the checks below return early on errors
+  int* h_status = h_status_v.data();
   SGX_CUDA(cudaMemcpyAsync(ms_done, a.ms_done, sizeof(int) * nch, cudaMemcpyDeviceToHost, s));
   SGX_CUDA(cudaMemcpyAsync(h_status, a.status, sizeof(int) * nch, cudaMemcpyDeviceToHost, s));
   SGX_CUDA(cudaStreamSynchronize(s));
@@ -1116,7 +1118,6 @@ extern "C" int sgx_track(const int8_t* rec, int64_t rec_stride, const int64_t* r
   int rc = SGX_OK;
   for (int i = 0; i < nch; ++i)
     if (h_status[i] != SGX_OK && rc == SGX_OK) rc = h_status[i];
-  free(h_status);
   if (rc == SGX_ERR_SHORT) return fail(rc, "sgx_track", "Not able to read the specified number of samples for tracking");
   if (rc != SGX_OK) return fail(rc, "sgx_track", "loop state left the supported range");
   return SGX_OK;
