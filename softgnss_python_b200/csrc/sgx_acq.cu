@@ -333,17 +333,21 @@ static int launch_pass(const fft::Plan& pl, int p, bool inverse, int batch, Pro 
     SGX_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem[p])); \
     SGX_COUNTED_LAUNCH(kfn, grid, dim3(fft::FFT_THREADS), pl.smem[p], s, P, pro, epi);            \
   }
-#define SGX_FFT_GOS(R0, R1)                                                                       \
+#define SGX_FFT_GOS(BIG, R0, R1)                                                                  \
   {                                                                                               \
-    auto kfn = fft::fft_pass_kernel<Pro, Epi, false, false, R0, R1>;                              \
+    auto kfn = fft::fft_pass_kernel<Pro, Epi, false, BIG, R0, R1>;                                \
     SGX_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem[p])); \
     SGX_COUNTED_LAUNCH(kfn, grid, dim3(fft::FFT_THREADS), pl.smem[p], s, P, pro, epi);            \
   }
   const bool pow2_fwd = !inverse && !pl.big && P.nsub == 2 && P.radix[0] == 16 &&
                         !(getenv("SGX_FFT_GENERIC") && getenv("SGX_FFT_GENERIC")[0] == '1');
-  if (pow2_fwd && P.radix[1] == 16) SGX_FFT_GOS(16, 16)
-  else if (pow2_fwd && P.radix[1] == 8) SGX_FFT_GOS(16, 8)
-  else if (pow2_fwd && P.radix[1] == 4) SGX_FFT_GOS(16, 4)
+  const bool big_fwd = !inverse && pl.big && P.nsub == 2 &&
+                       !(getenv("SGX_FFT_GENERIC") && getenv("SGX_FFT_GENERIC")[0] == '1');
+  if (pow2_fwd && P.radix[1] == 16) SGX_FFT_GOS(false, 16, 16)
+  else if (pow2_fwd && P.radix[1] == 8) SGX_FFT_GOS(false, 16, 8)
+  else if (pow2_fwd && P.radix[1] == 4) SGX_FFT_GOS(false, 16, 4)
+  else if (big_fwd && P.radix[0] == 31 && P.radix[1] == 7) SGX_FFT_GOS(true, 31, 7)      // forward search transforms
+  else if (big_fwd && P.radix[0] == 16 && P.radix[1] == 11) SGX_FFT_GOS(true, 16, 11)
   else if (inverse) { if (pl.big) SGX_FFT_GO(true, true) else SGX_FFT_GO(true, false) }
   else         { if (pl.big) SGX_FFT_GO(false, true) else SGX_FFT_GO(false, false) }
 #undef SGX_FFT_GO
