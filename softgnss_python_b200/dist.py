@@ -76,3 +76,35 @@ def track_sharded(recordings, rec_len, channel_sets, settings, stream=0):
     total = int(sum(int(c.item()) for c in counts))
     assert all(int(c.item()) == len(channel_sets) for c in counts), "equal shards expected"
     return rc, gather_results(out, total, axis=0), gather_results(done, total, axis=0)
+
+
+def gather_epochs(local, n_units):
+    """Gather per-recording arrays whose second axis is the measurement epoch (``[R_local, E_local, ...]``): the
+    epoch count differs between ranks (it follows from each recording's subframe start, postNavigation.py:199), so
+    the shards are first padded to the largest E -- NaN for floating point (the reference's initial value of a
+    solution column), 0 otherwise -- and then gathered in recording order."""
+    import torch
+    dist = _dist()
+    local = np.ascontiguousarray(local)
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return local
+    device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    e_max = torch.tensor([local.shape[1]], device=device)
+    dist.all_reduce(e_max, op=dist.ReduceOp.MAX)
+    e_max = int(e_max.item())
+    fill = np.nan if local.dtype.kind == "f" else 0
+    pad = np.full((local.shape[0], e_max) + local.shape[2:], fill, dtype=local.dtype)
+    pad[:, :local.shape[1]] = local
+    return gather_results(pad, n_units, axis=0)
+
+
+def post_navigate_sharded(track_out, prn, settings, n_total, stream=0):
+    """Preamble search -> ephemeris decoding -> measurement loop for this rank's recordings (``track_out`` is the
+    local shard of ``track_batch``'s output and stays on its GPU); the solutions of all ``n_total`` recordings are
+    gathered to every rank.  No exchange inside the chain: recordings are independent."""
+    from . import postnav
+    out = postnav.post_navigate_batch(track_out, prn, settings, stream=stream)
+    res = {k: gather_epochs(out[k], n_total) for k in ("sol", "rawP", "correctedP", "el", "az", "active")}
+    for k in ("n_epochs", "subFrameStart", "ready", "tow"):
+        res[k] = gather_results(out[k], n_total, axis=0)
+    return res

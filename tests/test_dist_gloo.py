@@ -28,7 +28,18 @@ def _worker(rank, world, port, q):
     trk = np.arange(4 * 2 * 13 * 5, dtype=np.float64).reshape(4, 2, 13, 5)  # 4 recordings total
     l2, h2 = sd.shard_range(4, rank, world)
     got2 = sd.gather_results(trk[l2:h2], 4, axis=0)
-    q.put((rank, np.array_equal(got, full), np.array_equal(got2, trk), (lo, hi)))
+    # navigation solutions: the epoch count differs per rank (ragged second axis), padded with NaN / 0
+    e_local = 3 if rank == 0 else 5
+    sol = np.full((h2 - l2, e_local, 12), float(rank + 1))
+    act = np.full((h2 - l2, e_local, 8), rank + 1, dtype=np.uint8)
+    gs, ga = sd.gather_epochs(sol, 4), sd.gather_epochs(act, 4)
+    ok3 = gs.shape == (4, 5, 12) and ga.shape == (4, 5, 8)
+    for r2 in range(world):
+        a, b = sd.shard_range(4, r2, world)
+        e2 = 3 if r2 == 0 else 5
+        ok3 = ok3 and np.all(gs[a:b, :e2] == r2 + 1) and np.all(np.isnan(gs[a:b, e2:]))
+        ok3 = ok3 and np.all(ga[a:b, :e2] == r2 + 1) and np.all(ga[a:b, e2:] == 0)
+    q.put((rank, np.array_equal(got, full), np.array_equal(got2, trk) and bool(ok3), (lo, hi)))
     dist.destroy_process_group()
 
 
