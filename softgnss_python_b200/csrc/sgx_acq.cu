@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "sgx_fft.cuh"
+#include "sgx_pfa.cuh"   // prime-factor search kernel for N = 31*7*16*11 (own translation unit)
 
 namespace sgx {
 using fft::cpx;
@@ -54,10 +55,6 @@ struct ProCode {  // A5: row of the sampled C/A table (tiled over coherent ms), 
   __device__ __forceinline__ cpx load(int i) const { return make_float2((float)table[i % n1], 0.f); }
 };
 
-struct SearchDims {
-  int nprn, nbins, blocks, prn_first;
-};
-
 struct ProMul {  // A7 first half: spectrum x conj(code spectrum); batch -> item = item0 + batch
   const cpx* spec;   // [rec][blk][bin][n]
   const cpx* codeF;  // [32][n]
@@ -74,11 +71,6 @@ struct ProMul {  // A7 first half: spectrum x conj(code spectrum); batch -> item
     codeF += (long long)(d.prn_first + prn) * n;
   }
   __device__ __forceinline__ cpx load(int i) const { return fft::cmulf(spec[i], codeF[i]); }
-};
-
-struct PeakSel {  // per (rec, prn): result of A8/A9 first half
-  int bin, blk, codePhase;
-  float peak;
 };
 
 struct ProMulSel {  // same product for the winning (bin, block) of PRN item (rec*nprn + prn)
@@ -187,17 +179,6 @@ struct EpiPeak {  // |.|^2 and arg-max of the whole row; one key per (item, tile
     if (threadIdx.x == 0) partial[(item0 + batch) * ntiles + tile] = k;
   }
 };
-
-// acquisition.py:147-159: is code phase i a candidate for the second peak?
-__device__ __forceinline__ bool second_peak_candidate(int i, int c, int w, int n) {
-  const int lo = c - w, hi = c + w;
-  if (lo <= 0) return i >= hi && i <= n + lo;  // (index n itself, the reference's IndexError, cannot occur)
-  if (hi >= n - 1) {
-    const int a = hi - n, b = lo - 1;           // a >= -1; -1 is numpy's "last element"
-    return (i >= a && i <= b) || (a < 0 && i == n + a);
-  }
-  return i <= lo || i >= hi;
-}
 
 struct EpiSecond {  // arg-max over the candidates only
   unsigned long long* partial;
@@ -505,6 +486,8 @@ struct AcqPlan {
   unsigned long long table_hash = 0;
   int n = 0, n1 = 0, nfft = 0, nvalid = 0;
   fft::Plan fwd, inv, fine;
+  bool pfa = false;     // search transforms through pfa_search_kernel (spectra stored in residue order)
+  DevBuf perm, scratch;
   DevBuf codeF, table, chips, fidx, cps, sig, spec, work0, work1, partial, partial2, sel, sums, metric, cph, fbin,
       fitems, fpartial, findex;
 };
@@ -517,6 +500,13 @@ static unsigned long long fnv(const void* p, size_t n, unsigned long long h = 14
   for (; i + 8 <= n; i += 8) { unsigned long long w; memcpy(&w, b + i, 8); h ^= w; h *= 1099511628211ULL; }
   for (; i < n; ++i) { h ^= b[i]; h *= 1099511628211ULL; }
   return h;
+}
+
+typedef pfa::SearchShape SearchShape;
+
+static bool pfa_enabled() {
+  const char* e = getenv("SGX_ACQ_PFA");
+  return !(e && e[0] == '0');
 }
 
 static int ensure_plan(const sgx_settings* st, const int8_t* ca_table, const int8_t* ca_chips,
@@ -554,10 +544,23 @@ static int ensure_plan(const sgx_settings* st, const int8_t* ca_table, const int
   }
   SGX_CUDA(cudaMemcpyAsync(a.cps.p, cps.data(), sizeof(double) * st->numFrqBins, cudaMemcpyHostToDevice, s));
   SGX_CUDA(cudaStreamSynchronize(s));
+  a.pfa = pfa_enabled() && a.n == SearchShape::N;
+  if (a.pfa) {
+    std::vector<int> perm(a.n);
+    for (int k = 0; k < a.n; ++k) perm[k] = SearchShape::storage_index(k);
+    if (a.perm.reserve(sizeof(int) * a.n)) return fail(SGX_ERR_CUDA, "cudaMalloc", "acquisition plan");
+    SGX_CUDA(cudaMemcpyAsync(a.perm.p, perm.data(), sizeof(int) * a.n, cudaMemcpyHostToDevice, s));
+    SGX_CUDA(cudaStreamSynchronize(s));
+  }
   // A5: conj(FFT(code)) / n for all 32 PRNs
-  rc = run_fft(a.fwd, false, 32, ProCode{a.table.as<int8_t>(), n1},
-               fft::StoreCpx{a.codeF.as<cpx>(), (long long)a.n, 1.0f / (float)a.n, 1, nullptr}, a.work0.as<cpx>(),
-               a.work1.as<cpx>(), s);
+  if (a.pfa)
+    rc = run_fft(a.fwd, false, 32, ProCode{a.table.as<int8_t>(), n1},
+                 pfa::StorePerm{a.codeF.as<cpx>(), (long long)a.n, 1.0f / (float)a.n, 1, a.perm.as<int>(), nullptr},
+                 a.work0.as<cpx>(), a.work1.as<cpx>(), s);
+  else
+    rc = run_fft(a.fwd, false, 32, ProCode{a.table.as<int8_t>(), n1},
+                 fft::StoreCpx{a.codeF.as<cpx>(), (long long)a.n, 1.0f / (float)a.n, 1, nullptr}, a.work0.as<cpx>(),
+                 a.work1.as<cpx>(), s);
   if (rc) return rc;
   a.valid = true;
   return SGX_OK;
@@ -631,11 +634,24 @@ extern "C" int sgx_acquire(const int8_t* sig, int64_t rec_stride, int64_t n_samp
   // ---- A6 + forward half of A7: one spectrum per (rec, block, bin) -----------------------------
   if (nspec > 32768 || npr > 32768)
     return fail(SGX_ERR_ARG, "sgx_acquire", "too many recordings in one call (split the batch)");
-  rc = run_fft(a.fwd, false, nspec, ProNco{d_sig, stride, a.cps.as<double>(), nbins, blocks, (int)n, 0.0},
-               fft::StoreCpx{a.spec.as<cpx>(), n, 1.f, 0, nullptr}, a.work0.as<cpx>(), a.work1.as<cpx>(), s);
+  if (a.pfa)
+    rc = run_fft(a.fwd, false, nspec, ProNco{d_sig, stride, a.cps.as<double>(), nbins, blocks, (int)n, 0.0},
+                 pfa::StorePerm{a.spec.as<cpx>(), n, 1.f, 0, a.perm.as<int>(), nullptr}, a.work0.as<cpx>(), a.work1.as<cpx>(), s);
+  else
+    rc = run_fft(a.fwd, false, nspec, ProNco{d_sig, stride, a.cps.as<double>(), nbins, blocks, (int)n, 0.0},
+                 fft::StoreCpx{a.spec.as<cpx>(), n, 1.f, 0, nullptr}, a.work0.as<cpx>(), a.work1.as<cpx>(), s);
   if (rc) return rc;
-  // ---- A7: spectrum x code -> IFFT -> |.|^2 -> per-row arg-max, in L2-sized chunks -------------
-  for (long long i0 = 0; i0 < nitems; i0 += chunk) {
+  const int nt_keys = a.pfa ? 1 : nt_last;   // keys per transform: the prime-factor kernel reduces the whole row itself
+  // ---- A7: spectrum x code -> IFFT -> |.|^2 -> per-row arg-max ---------------------------------
+  if (a.pfa) {
+    pfa::SearchArgs sa;
+    sa.spec = a.spec.as<cpx>(); sa.codeF = a.codeF.as<cpx>(); sa.scratch = nullptr;
+    sa.partial = a.partial.as<unsigned long long>(); sa.sel = nullptr; sa.sel_out = nullptr; sa.d = d; sa.nitems = nitems;
+    sa.chip = st->samplesPerCodeChip;
+    rc = pfa::launch_search(sa, false, a.scratch, s);
+    if (rc) return rc;
+  } else
+  for (long long i0 = 0; i0 < nitems; i0 += chunk) {   // in L2-sized chunks
     const int cnt = (int)((nitems - i0) < chunk ? (nitems - i0) : chunk);
     EpiPeak ep;
     ep.partial = a.partial.as<unsigned long long>(); ep.ntiles = nt_last; ep.item0 = i0; ep.best = 0; ep.n1 = n1;
@@ -648,9 +664,16 @@ extern "C" int sgx_acquire(const int8_t* sig, int64_t rec_stride, int64_t n_samp
     if (rc) return rc;
   }
   // ---- A8 + A9 -------------------------------------------------------------------------------
-  SGX_COUNTED_LAUNCH(select_kernel, dim3(npr), dim3(128), 0, s, a.partial.as<unsigned long long>(), nt_last, d,
+  SGX_COUNTED_LAUNCH(select_kernel, dim3(npr), dim3(128), 0, s, a.partial.as<unsigned long long>(), nt_keys, d,
                      a.sel.as<PeakSel>());
-  {
+  if (a.pfa) {
+    pfa::SearchArgs sa;
+    sa.spec = a.spec.as<cpx>(); sa.codeF = a.codeF.as<cpx>(); sa.scratch = nullptr;
+    sa.partial = a.partial2.as<unsigned long long>(); sa.sel = a.sel.as<PeakSel>(); sa.sel_out = a.sel.as<PeakSel>(); sa.d = d; sa.nitems = npr;
+    sa.chip = st->samplesPerCodeChip;
+    rc = pfa::launch_search(sa, true, a.scratch, s);
+    if (rc) return rc;
+  } else {
     EpiSecond es;
     es.partial = a.partial2.as<unsigned long long>(); es.sel = a.sel.as<PeakSel>(); es.ntiles = nt_last;
     es.chip = st->samplesPerCodeChip; es.n = n1; es.best = 0; es.cp = 0;   // candidates within one code period
@@ -663,7 +686,7 @@ extern "C" int sgx_acquire(const int8_t* sig, int64_t rec_stride, int64_t n_samp
     if (rc) return rc;
   }
   SGX_COUNTED_LAUNCH(metric_kernel, dim3((npr + 127) / 128), dim3(128), 0, s, a.partial2.as<unsigned long long>(),
-                     nt_last, a.sel.as<PeakSel>(), npr, a.metric.as<double>(), a.cph.as<int>(), a.fbin.as<int>());
+                     nt_keys, a.sel.as<PeakSel>(), npr, a.metric.as<double>(), a.cph.as<int>(), a.fbin.as<int>());
   SGX_CUDA(cudaGetLastError());
   std::vector<int> h_cph_v((size_t)npr * 2);   // host staging is RAII: the SGX_CUDA checks below return early on errors
   int* h_cph = h_cph_v.data();

@@ -15,6 +15,13 @@
 
 #include "../../include/softgnss_b200.h"
 
+// constant tables in headers shared by several translation units: internal linkage
+#ifdef SGX_EMUL
+#define SGX_TABLE static
+#else
+#define SGX_TABLE static __constant__
+#endif
+
 namespace sgx {
 
 extern char g_err[512];

@@ -513,7 +513,7 @@ __device__ __forceinline__ unsigned long long block_max_key(unsigned long long k
 }
 
 // ---- twiddle / table setup --------------------------------------------------------------------
-__global__ void twiddle_kernel(cpx* out, long long count, int Ls, long long M) {
+static __global__ void twiddle_kernel(cpx* out, long long count, int Ls, long long M) {
   // Ls > 0: out[t*Ls + k] = exp(-2*pi*i * (t*k mod M) / M);   Ls == 0: out[q] = exp(-2*pi*i*q/M)
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < count;
        e += (long long)gridDim.x * blockDim.x) {

@@ -1,0 +1,387 @@
+// Prime-factor search kernel (see sgx_pfa.cuh) -- its own translation unit so that it builds in seconds.
+#include "sgx_pfa.cuh"
+#include "sgx_pfa_tables.h"
+
+namespace sgx {
+namespace pfa {
+
+// ---- radix-31 inverse butterfly in three rolled groups of five output pairs --------------------------------------
+// The fully unrolled conjugate-pair butterfly is ~1100 instructions (17 KB); sixteen unsynchronised warps streaming
+// through it (and the rest of a 62 KB kernel) miss the 32 KB L1.5 instruction cache all the time
+// (profiles/ncu_summary_r2_v1.md: `no_instruction` 1.5 stalled warps per issue).  With the pairs taken in the order of
+// the powers of the primitive root 3, cos(2 pi j_n k_m / 31) = C[(n + m) mod 15]: the 15 x 15 cosine matrix is a
+// circulant (the sine matrix a skew-circulant), so output group q = 0, 1, 2 is the same straight-line code applied to
+// the pair arrays rotated by 5 q places -- 400 instructions executed three times, plus 2 x 60 register moves.
+struct R31 {
+  cpx A[15], B[15];   // a'_n = x[j_n] + x[31 - j_n],  b'_n = sg_n (x[j_n] - x[31 - j_n])
+  cpx x0;
+  // v: spectrum values, y: code-spectrum values (row stride ys); returns the DC output
+  __device__ __forceinline__ cpx prepare(const cpx* v, const cpx* y, int ys) {
+    constexpr int J[15] = SGX_R31_J;
+    constexpr int SG[15] = SGX_R31_SG;
+    x0 = fft::cmulf(v[0], y[0]);
+    cpx dc = x0;
+#pragma unroll
+    for (int n = 0; n < 15; ++n) {
+      const cpx p = fft::cmulf(v[J[n]], y[J[n] * ys]), q = fft::cmulf(v[31 - J[n]], y[(31 - J[n]) * ys]);
+      A[n] = fft::cadd(p, q);
+      B[n] = SG[n] > 0 ? fft::csub(p, q) : fft::csub(q, p);
+      dc = fft::cadd(dc, A[n]);
+    }
+    return dc;
+  }
+  // output pair r of the current group: hi -> row KHI31[5 q + r], lo -> row 31 - KHI31[5 q + r]
+  template <int r>
+  __device__ __forceinline__ void pair(cpx& hi, cpx& lo) const {
+    float cr = x0.x, ci = x0.y, sr = 0.f, si = 0.f;
+#pragma unroll
+    for (int n = 0; n < 15; ++n) {
+      const float c = C31R[(n + r) % 15], s = S31R[n + r];
+      cr = fmaf(A[n].x, c, cr);
+      ci = fmaf(A[n].y, c, ci);
+      sr = fmaf(B[n].x, s, sr);
+      si = fmaf(B[n].y, s, si);
+    }
+    hi = make_float2(cr - si, ci + sr);
+    lo = make_float2(cr + si, ci - sr);
+  }
+  __device__ __forceinline__ void rotate() {   // A_n <- A_(n-5 mod 15);  B_n <- B_(n-5), antiperiodic
+    cpx tA[15], tB[15];
+#pragma unroll
+    for (int n = 0; n < 15; ++n) {
+      tA[n] = A[(n + 10) % 15];
+      tB[n] = n < 5 ? make_float2(-B[n + 10].x, -B[n + 10].y) : B[n - 5];
+    }
+#pragma unroll
+    for (int n = 0; n < 15; ++n) { A[n] = tA[n]; B[n] = tB[n]; }
+  }
+};
+
+// Pass B of one transform for one warp: DFT over (k4, k3) of its slices of 8 tauA columns, read from the scratch.
+// MODE 0: maximum of |.|^2 only (hot path: 3 instructions per point; the code phase of the winning row is found by the
+//         masked kernel, which recomputes that row anyway);
+// MODE 1: exact arg-max, smallest index among equal values (numpy's rule);
+// MODE 2: maximum over the second-peak candidates of acquisition.py:147-159 around code phase cp.
+template <class S, int WARPS, int MODE>
+__device__ __forceinline__ void pass_b(const cpx* scr, cpx* X, int w, int lane, int cp, int chip, float& best, int& bidx) {
+  constexpr int P2 = S::p2, P3 = S::p3, P4 = S::p4;
+  constexpr int NA = S::NA, N = S::N, SROW = S::SROW, CB = S::CB, KB = 32 / CB;
+  constexpr int Q1 = N / S::p1, Q2 = N / P2, Q3 = N / P3, Q4 = N / P4;
+  const int jb = lane & (CB - 1), kb = lane / CB;
+  cpx ua[P4], ub[P4];
+  {  // first round of the first slice
+    const int tA = w * CB + jb;
+    const cpx* p = scr + (size_t)(kb * P4) * SROW + (tA < NA ? tA : 0);
+#pragma unroll
+    for (int k4 = 0; k4 < P4; ++k4) ua[k4] = __ldcg(p + (size_t)k4 * SROW);
+  }
+#pragma unroll 1
+  for (int sb = w; sb < S::NSB; sb += WARPS) {
+    const int tA = sb * CB + jb;
+    const bool valid = tA < NA;
+    // stage 1 (radix P4 over k4): lane (k3 = kb + KB*r, column jb); tile rows k3*P4 + k4 -> k3*P4 + tau4.
+    // Two register sets: the loads of round r+1 are in flight while round r is computed.
+    {
+      const cpx* p = scr + (size_t)(kb * P4) * SROW + (valid ? tA : 0);
+      cpx* rp = X + (kb * P4) * CB + jb;
+#pragma unroll 1
+      for (int r = 0; r < 4; r += 2) {
+#pragma unroll
+        for (int k4 = 0; k4 < P4; ++k4) ub[k4] = __ldcg(p + (size_t)((r + 1) * KB * P4 + k4) * SROW);
+        fft::Dft<P4, true>::run(ua);
+#pragma unroll
+        for (int t4 = 0; t4 < P4; ++t4) rp[(r * KB * P4 + t4) * CB] = ua[t4];
+        if (r + 2 < 4) {
+#pragma unroll
+          for (int k4 = 0; k4 < P4; ++k4) ua[k4] = __ldcg(p + (size_t)((r + 2) * KB * P4 + k4) * SROW);
+        }
+        fft::Dft<P4, true>::run(ub);
+#pragma unroll
+        for (int t4 = 0; t4 < P4; ++t4) rp[((r + 1) * KB * P4 + t4) * CB] = ub[t4];
+      }
+    }
+    __syncwarp();
+    if (sb + WARPS < S::NSB) {   // first round of the next slice travels during stage 2
+      const int tn = (sb + WARPS) * CB + jb;
+      const cpx* p = scr + (size_t)(kb * P4) * SROW + (tn < NA ? tn : 0);
+#pragma unroll
+      for (int k4 = 0; k4 < P4; ++k4) ua[k4] = __ldcg(p + (size_t)k4 * SROW);
+    }
+    // stage 2 (radix P3 over k3): lane (tau4 = kb + KB*r, column jb); outputs stay in registers
+    const int baseA = valid ? ((tA / P2) * Q1 + (tA % P2) * Q2) % N : 0;
+#pragma unroll 1
+    for (int t4 = kb; t4 < P4; t4 += KB) {
+      if (valid) {
+        cpx u[P3];
+        const cpx* rp = X + t4 * CB + jb;
+#pragma unroll
+        for (int k3 = 0; k3 < P3; ++k3) u[k3] = rp[(k3 * P4) * CB];
+        fft::Dft<P3, true>::run(u);
+        if (MODE == 0) {
+#pragma unroll
+          for (int t3 = 0; t3 < P3; ++t3) best = fmaxf(best, fmaf(u[t3].x, u[t3].x, u[t3].y * u[t3].y));
+        } else {
+          int tau = (baseA + t4 * Q4) % N;
+#pragma unroll
+          for (int t3 = 0; t3 < P3; ++t3) {
+            const float mag = fmaf(u[t3].x, u[t3].x, u[t3].y * u[t3].y);
+            const bool cand = MODE == 1 || second_peak_candidate(tau, cp, chip, N);
+            if (cand && (mag > best || (mag == best && tau < bidx))) { best = mag; bidx = tau; }
+            tau += Q3;
+            if (tau >= N) tau -= N;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <int WARPS>
+__device__ __forceinline__ unsigned long long block_max(unsigned long long key, unsigned long long* red, int w, int lane) {
+#pragma unroll
+  for (int msk = 16; msk > 0; msk >>= 1) {
+    const unsigned long long o = __shfl_xor_sync(0xffffffffu, key, msk);
+    key = o > key ? o : key;
+  }
+  if (lane == 0) red[w] = key;
+  __syncthreads();
+  unsigned long long k = red[0];
+#pragma unroll
+  for (int i = 1; i < WARPS; ++i) k = red[i] > k ? red[i] : k;
+  return k;
+}
+
+// Hot kernel (MASKED = false): one key (maximum of |.|^2, index field unused) per transform.
+// MASKED: one transform per (rec, prn), the winning (bin, block) of select_kernel: the code phase (exact arg-max) is
+// written to sel[].codePhase, the key of the second peak (acquisition.py:147-162) to partial[].
+//
+// Warp-independent slices: in pass A a warp owns 4 columns (kB values) x all NA rows, in pass B 8 columns (tauA
+// values) x all NB rows; every butterfly stage of a slice reads only what the same warp wrote, so the only
+// block-wide barriers are the two per transform (pass A -> pass B; key reduction / scratch reuse).
+// Per warp two shared-memory buffers of NA x 4 values: X (work tile) and Y (code-spectrum slice, filled by cp.async
+// one slice ahead); the spectrum slice of the next slice travels in registers while the current one goes through
+// its second stage and the scratch store.  Pass B uses X and Y together as one NB x 8 tile.
+template <int P1, int P2, int P3, int P4, int WARPS, int MINB, bool MASKED>
+__global__ void __launch_bounds__(WARPS * 32, MINB) pfa_search_kernel(SearchArgs a) {
+  typedef Shape<P1, P2, P3, P4> S;
+  static_assert(P1 == 31, "stage 1 is the grouped radix-31 butterfly");
+  constexpr int NA = S::NA, NB = S::NB, N = S::N, SROW = S::SROW;
+  constexpr int CA = S::CA, CB = S::CB;            // columns per warp slice
+  constexpr int KA = 32 / CA, KB = 32 / CB;        // butterflies per warp round
+  static_assert(CA == 4 && P3 / KB == 4, "copy loops / register ping-pong");
+  SGX_DYN_SMEM(smem);
+  __shared__ unsigned long long red[2][WARPS];
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  cpx* X = reinterpret_cast<cpx*>(smem) + (size_t)w * S::WARP_TILE;
+  cpx* Y = X + NA * CA;
+  cpx* scr = a.scratch + (size_t)blockIdx.x * NB * SROW;
+  const int ja = lane & (CA - 1), ka = lane / CA;
+  const bool act = ka < P2;
+  const size_t off0 = (size_t)(act ? ka : 0) * NB + ja;
+
+  const cpx* src = nullptr;
+  const cpx* cod = nullptr;
+  long long out_index = 0;
+  auto locate = [&](long long item) {
+    if (!MASKED) {   // PRN fastest: the CTAs running at any moment share a handful of spectra and the 32 code spectra
+      long long t = item;
+      const int prn = (int)(t % a.d.nprn); t /= a.d.nprn;
+      const int blk = (int)(t % a.d.blocks); t /= a.d.blocks;
+      const int bin = (int)(t % a.d.nbins);
+      const int rec = (int)(t / a.d.nbins);
+      src = a.spec + (((long long)rec * a.d.blocks + blk) * a.d.nbins + bin) * N;
+      cod = a.codeF + (long long)(a.d.prn_first + prn) * N;
+      out_index = (((long long)rec * a.d.nprn + prn) * a.d.nbins + bin) * a.d.blocks + blk;
+    } else {
+      const PeakSel s = a.sel[item];
+      const int prn = (int)(item % a.d.nprn), rec = (int)(item / a.d.nprn);
+      src = a.spec + (((long long)rec * a.d.blocks + s.blk) * a.d.nbins + s.bin) * N;
+      cod = a.codeF + (long long)(a.d.prn_first + prn) * N;
+      out_index = item;
+    }
+  };
+  cpx v[P1];
+  // code slice `sa` -> Y (two 16-byte copies per row), spectrum slice -> registers
+  auto fetch = [&](int sa) {
+    const cpx* q = cod + sa * CA;
+#pragma unroll 1
+    for (int i = lane; i < 2 * NA; i += 32) cp_async16(Y + (i >> 1) * CA + (i & 1) * 2, q + (size_t)(i >> 1) * NB + (i & 1) * 2);
+    cp_async_commit();
+    if (act) {
+      const cpx* p = src + off0 + sa * CA;
+#pragma unroll
+      for (int k1 = 0; k1 < P1; ++k1) v[k1] = __ldg(p + (size_t)k1 * P2 * NB);
+    }
+  };
+
+#pragma unroll 1
+  for (long long item = blockIdx.x; item < a.nitems; item += gridDim.x) {
+    locate(item);
+    if (w < S::NSA) fetch(w);
+    // ---------------- pass A: DFT over (k1, k2); slice = CA values of kB = k3*P4 + k4 --------------------------------
+#pragma unroll 1
+    for (int sa = w; sa < S::NSA; sa += WARPS) {
+      cp_async_wait_all();
+      __syncwarp();
+      // stage 1 (radix 31): lane (k2 = ka, column ja); rows k1*P2 + k2 -> tau1*P2 + k2
+      if (act) {
+        R31 bf;
+        cpx* x = X + ka * CA + ja;
+        x[0] = bf.prepare(v, Y + ka * CA + ja, P2 * CA);
+#pragma unroll 1
+        for (int q = 0; q < 3; ++q) {
+          cpx hi, lo;
+#define SGX_R31_PAIR(r)                                        \
+  {                                                            \
+    bf.pair<r>(hi, lo);                                        \
+    const int kh = KHI31[q * 5 + r];                           \
+    x[kh * (P2 * CA)] = hi;                                    \
+    x[(P1 - kh) * (P2 * CA)] = lo;                             \
+  }
+          SGX_R31_PAIR(0) SGX_R31_PAIR(1) SGX_R31_PAIR(2) SGX_R31_PAIR(3) SGX_R31_PAIR(4)
+#undef SGX_R31_PAIR
+          if (q < 2) bf.rotate();
+        }
+      }
+      __syncwarp();
+      // the next slice's operands travel while this slice goes through stage 2 and the scratch store
+      if (sa + WARPS < S::NSA) fetch(sa + WARPS);
+      // stage 2 (radix P2): lane (tau1 = ka + KA*r, column ja), in place
+#pragma unroll 1
+      for (int t1 = ka; t1 < P1; t1 += KA) {
+        cpx u[P2];
+        cpx* rp = X + (t1 * P2) * CA + ja;
+#pragma unroll
+        for (int k2 = 0; k2 < P2; ++k2) u[k2] = rp[k2 * CA];
+        fft::Dft<P2, true>::run(u);
+#pragma unroll
+        for (int t2 = 0; t2 < P2; ++t2) rp[t2 * CA] = u[t2];
+      }
+      __syncwarp();
+      // tile row c = tauA holds the 4 columns of this slice; a lane pair takes a row (16 bytes each), column j goes to
+      // scratch row kB = sa*4 + j
+      {
+        cpx* dst = scr + (size_t)(sa * CA + (lane & 1) * 2) * SROW;
+#pragma unroll 1
+        for (int c = lane >> 1; c < NA; c += 16) {
+          const float4 x = *reinterpret_cast<const float4*>(X + c * CA + (lane & 1) * 2);
+          __stcg(dst + c, make_float2(x.x, x.y));
+          __stcg(dst + SROW + c, make_float2(x.z, x.w));
+        }
+      }
+      __syncwarp();
+    }
+    __syncthreads();   // the whole intermediate is in the scratch (and visible to the block)
+    // ---------------- pass B ------------------------------------------------------------------------------------------
+    if (!MASKED) {
+      float best = 0.f;
+      int unused = 0;
+      pass_b<S, WARPS, 0>(scr, X, w, lane, 0, 0, best, unused);
+      // (the barrier inside: every warp is done reading the scratch before the next transform overwrites it)
+      const unsigned long long k = block_max<WARPS>(fft::peak_key(best, 0u), red[0], w, lane);
+      if (tid == 0) a.partial[out_index] = k;
+    } else {
+      float best = -1.f;
+      int bidx = 0x7fffffff;
+      pass_b<S, WARPS, 1>(scr, X, w, lane, 0, 0, best, bidx);
+      const unsigned long long k1 = block_max<WARPS>(best >= 0.f ? fft::peak_key(best, (unsigned)bidx) : 0ull, red[0], w, lane);
+      const int cp = (int)fft::key_index(k1);
+      best = -1.f;
+      bidx = 0x7fffffff;
+      pass_b<S, WARPS, 2>(scr, X, w, lane, cp, a.chip, best, bidx);
+      const unsigned long long k2 = block_max<WARPS>(best >= 0.f ? fft::peak_key(best, (unsigned)bidx) : 0ull, red[1], w, lane);
+      if (tid == 0) {
+        a.partial[out_index] = k2;
+        a.sel_out[out_index].codePhase = cp;
+        a.sel_out[out_index].peak = fft::key_value(k1);
+      }
+    }
+  }
+}
+
+template <int WARPS, int MINB, bool MASKED>
+static int launch_cfg(SearchArgs args, DevBuf& scratch, cudaStream_t s) {
+  typedef SearchShape S;
+  int dev = 0, n_sm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  if (n_sm <= 0) n_sm = 148;
+  auto kfn = pfa_search_kernel<31, 7, 16, 11, WARPS, MINB, MASKED>;
+  const size_t smem = S::smem_per_warp * WARPS;
+  SGX_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, WARPS * 32, smem) != cudaSuccess || occ < 1) occ = 1;
+  if (occ > MINB) occ = MINB;
+  long long grid = (long long)n_sm * occ;
+  if (grid > args.nitems) grid = args.nitems;
+  const size_t bytes = S::scratch_per_cta * (size_t)grid;
+  if (scratch.reserve(bytes)) return fail(SGX_ERR_CUDA, "cudaMalloc", "search scratch");
+  args.scratch = scratch.as<cpx>();
+#ifdef SGX_EMUL
+  SGX_COUNTED_LAUNCH(kfn, dim3((unsigned)grid), dim3(WARPS * 32), smem, s, args);
+#else
+  // The scratch is rewritten and re-read by its CTA for every transform: keep it in L2 (persisting access window), so
+  // that the streamed spectra do not push it out to HBM.
+  static int persist_max = -1, window_max = 0;
+  const char* pe = getenv("SGX_PFA_PERSIST");
+  const bool want_persist = pe && pe[0] == '1';
+  if (persist_max < 0) {
+    persist_max = 0;
+    if (want_persist) {   // the set-aside shrinks the L2 available to everything else: only when asked for
+      cudaDeviceGetAttribute(&persist_max, cudaDevAttrMaxPersistingL2CacheSize, dev);
+      cudaDeviceGetAttribute(&window_max, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+      if (const char* f = getenv("SGX_PFA_PERSIST_MB")) { if (atoi(f) > 0 && ((long long)atoi(f) << 20) < persist_max) persist_max = atoi(f) << 20; }
+      if (persist_max > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)persist_max);
+      if (getenv("SGX_DEBUG")) fprintf(stderr, "[sgx debug] persisting L2 max %d B, window max %d B\n", persist_max, window_max);
+      cudaGetLastError();
+    }
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(WARPS * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  int nattr = 0;
+  if (want_persist && persist_max > 0 && window_max > 0) {
+    const size_t win = bytes < (size_t)window_max ? bytes : (size_t)window_max;
+    attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[0].val.accessPolicyWindow.base_ptr = scratch.p;
+    attr[0].val.accessPolicyWindow.num_bytes = win;
+    attr[0].val.accessPolicyWindow.hitRatio = win <= (size_t)persist_max ? 1.0f : (float)((double)persist_max / (double)win);
+    attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    nattr = 1;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = nattr;
+  SGX_CUDA(cudaLaunchKernelEx(&cfg, kfn, args));
+  ++g_launches;
+#endif
+  SGX_CUDA(cudaGetLastError());
+  return SGX_OK;
+}
+
+template <bool MASKED>
+static int launch_search_t(SearchArgs args, DevBuf& scratch, cudaStream_t s) {
+  int cfg = 62;   // warps per CTA x CTAs per SM
+  if (const char* e = getenv("SGX_PFA_CFG")) cfg = atoi(e);
+  switch (cfg) {
+    case 43: return launch_cfg<4, 3, MASKED>(args, scratch, s);
+    case 72: return launch_cfg<7, 2, MASKED>(args, scratch, s);
+    case 82: return launch_cfg<8, 2, MASKED>(args, scratch, s);
+    case 121: return launch_cfg<12, 1, MASKED>(args, scratch, s);
+    case 141: return launch_cfg<14, 1, MASKED>(args, scratch, s);
+    case 161: return launch_cfg<16, 1, MASKED>(args, scratch, s);
+    default: return launch_cfg<6, 2, MASKED>(args, scratch, s);
+  }
+}
+
+int launch_search(SearchArgs args, bool masked, DevBuf& scratch, cudaStream_t s) {
+  if (args.nitems <= 0) return SGX_OK;
+  return masked ? launch_search_t<true>(args, scratch, s) : launch_search_t<false>(args, scratch, s);
+}
+
+}  // namespace pfa
+}  // namespace sgx

@@ -84,6 +84,8 @@ struct BlockCtx {
   int alive = 0;
   int bar_arrived = 0;
   int bar_gen = 0;
+  int nbar_arrived[16] = {0};
+  int nbar_gen[16] = {0};
   dim3 grid, block;
   uint3_ bidx;
   const std::function<void()>* body = nullptr;
@@ -115,6 +117,7 @@ inline void run_block(BlockCtx& c) {
   const int n = (int)c.fibers.size();
   c.alive = n;
   c.bar_arrived = 0;
+  for (int i = 0; i < 16; ++i) c.nbar_arrived[i] = 0;
   for (auto& w : c.warps) { w = WarpState(); }
   for (int i = 0; i < n; ++i) {
     Fiber& f = c.fibers[i];
@@ -198,6 +201,18 @@ inline void syncthreads() {
   for (;;) {
     if (c->bar_gen != my) break;
     if (c->bar_arrived >= c->alive) { c->bar_arrived = 0; c->bar_gen++; break; }
+    yield_to_sched();
+  }
+}
+
+// bar.sync id, count: a barrier among `count` threads of the block (the callers partition the block statically)
+inline void named_barrier(int id, int count) {
+  BlockCtx* c = g_ctx;
+  int my = c->nbar_gen[id];
+  c->nbar_arrived[id]++;
+  for (;;) {
+    if (c->nbar_gen[id] != my) break;
+    if (c->nbar_arrived[id] >= count) { c->nbar_arrived[id] = 0; c->nbar_gen[id]++; break; }
     yield_to_sched();
   }
 }
@@ -309,6 +324,8 @@ static inline unsigned long long __umul64hi(unsigned long long a, unsigned long 
   return (unsigned long long)(((unsigned __int128)a * b) >> 64);
 }
 template <class T> static inline T __ldg(const T* p) { return *p; }
+template <class T> static inline T __ldcg(const T* p) { return *p; }
+template <class T> static inline void __stcg(T* p, T v) { *p = v; }
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 static inline float __fdividef(float a, float b) { return a / b; }
 using std::max;

@@ -1,0 +1,9 @@
+# round 2, call e: search kernel v4 -- configuration sweep (warps x CTAs/SM, L2 persistence), DRAM bytes per config
+O=gpurun_out/r2e; mkdir -p $O
+timeout 600 python -m pytest tests/test_gpu_acquisition.py tests/test_gpu_configs.py -m gpu -x -q > $O/pytest_acq.log 2>&1; echo "acq tests rc=$?" | tee $O/summary.txt; tail -3 $O/pytest_acq.log | tee -a $O/summary.txt
+for cfg in 62 43 72 82 121 141 161; do for pers in 1 0; do
+  echo "--- cfg=$cfg persist=$pers" | tee -a $O/summary.txt
+  SGX_PFA_CFG=$cfg SGX_PFA_PERSIST=$pers python tools/quick_acq_bench.py 32 2>&1 | tail -1 | tee -a $O/summary.txt
+  SGX_PFA_CFG=$cfg SGX_PFA_PERSIST=$pers timeout 120 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active --clock-control none -k regex:pfa_search_kernel -s 2 -c 1 --csv python tools/quick_acq_bench.py 32 2>/dev/null | grep -E "pfa_search" | awk -F'","' '{print $(NF-2), $(NF)}' | tr -d '"' | tr '\n' ';' | tee -a $O/summary.txt; echo | tee -a $O/summary.txt
+done; done
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:pfa_search_kernel -s 2 -c 1 -o $O/pfa python tools/quick_acq_bench.py 32 > $O/ncu_pfa.log 2>&1; echo "ncu rc=$?" | tee -a $O/summary.txt
