@@ -89,7 +89,14 @@ int sgx_abi_version(void);
 const char* sgx_last_error(void);
 /* Number of CUDA devices (0 if none / driver missing). */
 int sgx_device_count(void);
+/* Selects the device of this process.  The library keeps its plan caches and scratch buffers process-wide on ONE
+ * device (one process per GPU, as torch.distributed launches them): once a compute entry point has run, selecting a
+ * different device -- or calling a compute entry point while another device is current -- returns SGX_ERR_ARG.
+ * Compute entry points are serialised by a process-wide mutex (safe, not concurrent, from several host threads). */
 int sgx_set_device(int device);
+/* Measured FP32 FMA throughput of the current device (FFMA burn, 16 independent chains per thread), TFLOP/s: the
+ * denominator of the acquisition roofline in bench.py ("must measure an FMA-burn peak"). */
+int sgx_fp32_peak(double* tflops, void* cuda_stream);
 /* Kernels launched by this library in this process since load (bench.py's gpu_launches). */
 int64_t sgx_kernel_launch_count(void);
 

@@ -18,7 +18,7 @@ TRACK_FIELDS = ("absoluteSample", "codeFreq", "carrFreq", "I_P", "I_E", "I_L", "
                 "dllDiscr", "dllDiscrFilt", "pllDiscr", "pllDiscrFilt")
 SGX_ERR_SHORT = -3
 
-EXPORTS = ("sgx_abi_version", "sgx_last_error", "sgx_device_count", "sgx_set_device",
+EXPORTS = ("sgx_abi_version", "sgx_last_error", "sgx_device_count", "sgx_set_device", "sgx_fp32_peak",
            "sgx_kernel_launch_count", "sgx_acquire", "sgx_track", "sgx_synth_generate", "sgx_fft_c2c",
            "sgx_find_preambles", "sgx_pseudoranges", "sgx_nav_solve")
 
@@ -98,6 +98,13 @@ class Lib(object):
 
     def launches(self):
         return int(self.dll.sgx_kernel_launch_count())
+
+    def fp32_peak(self, stream=0):
+        """Measured FP32 FMA-burn throughput of the current device, TFLOP/s."""
+        self.require_device()
+        v = ctypes.c_double(0.0)
+        self.check(self.dll.sgx_fp32_peak(ctypes.byref(v), ctypes.c_void_p(stream)))
+        return float(v.value)
 
     # ------------------------------------------------------------------ tracking
     def track(self, rec, rec_stride, rec_len, channels, pod, ca_chips, out, stream=0):

@@ -17,6 +17,7 @@ from .tracking import Result
 
 
 _TABLES = {}
+ACQ_SPECTRA_BYTES = 24 << 30     # device memory one call may use for the spectra (the search work buffers come on top)
 
 
 def _tables(settings, fine_ms):
@@ -48,11 +49,19 @@ def acquire_batch(signals, settings, prn_first=0, prn_count=None, stream=0, diag
     fbin = np.zeros((r, prn_count), dtype=np.int32)
     fine = np.zeros((r, prn_count), dtype=np.int32)
     import ctypes
-    rc = L.dll.sgx_acquire(_native._ptr(signals), int(stride), ns, r, ctypes.byref(pod), _native._ptr(table),
-                           _native._ptr(chips), _native._ptr(fidx), int(prn_first),
-                           int(prn_count), _native._ptr(carr), _native._ptr(cph), _native._ptr(met),
-                           _native._ptr(fbin), _native._ptr(fine), ctypes.c_void_p(stream))
-    L.check(rc)
+    # one sgx_acquire call holds the wiped-off spectra of all its recordings (blocks x bins x n complex64 each):
+    # large batches (BASELINE config 3: 141 bins x 10 ms) are walked in slices of recordings
+    per_rec = int(pod.acqNonCoherentBlocks) * int(pod.numFrqBins)
+    spec_bytes = per_rec * int(pod.samplesPerCode) * int(pod.acqCoherentMs) * 8
+    rmax = max(1, min(32768 // per_rec, ACQ_SPECTRA_BYTES // spec_bytes, 32768 // prn_count))
+    for r0 in range(0, r, rmax):
+        r1 = min(r, r0 + rmax)
+        rc = L.dll.sgx_acquire(_native._ptr(signals[r0:r1]), int(stride), ns, r1 - r0, ctypes.byref(pod),
+                               _native._ptr(table), _native._ptr(chips), _native._ptr(fidx), int(prn_first),
+                               int(prn_count), _native._ptr(carr[r0:r1]), _native._ptr(cph[r0:r1]),
+                               _native._ptr(met[r0:r1]), _native._ptr(fbin[r0:r1]), _native._ptr(fine[r0:r1]),
+                               ctypes.c_void_p(stream))
+        L.check(rc)
     out = dict(carrFreq=carr, codePhase=cph, peakMetric=met)
     if diagnostics:
         out.update(frqBin=fbin, finePeakIndex=fine)

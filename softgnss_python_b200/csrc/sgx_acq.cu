@@ -241,35 +241,53 @@ __global__ void sum_kernel(const int8_t* sig, long long rec_stride, long long n,
 }
 
 // A8 + first half of A9 for one (rec, prn): block choice per bin, global peak, bin and code phase.
+// One block per (rec, prn); a thread takes bins tid, tid + blockDim.x, ... (any number of bins x blocks).
 __global__ void select_kernel(const unsigned long long* partial, int ntiles, SearchDims d, PeakSel* sel) {
   const int item = blockIdx.x;  // rec * nprn + prn
-  __shared__ unsigned long long row[512];  // [bin][blk], nbins*blocks <= 512
-  const int rows = d.nbins * d.blocks;
-  for (int r = threadIdx.x; r < rows; r += blockDim.x) {
-    const unsigned long long* p = partial + ((long long)item * rows + r) * ntiles;
+  __shared__ float s_v[128];
+  __shared__ int s_bin[128], s_blk[128];
+  __shared__ unsigned s_cp[128];
+  float peak = -1.f;
+  int fbin = 0x7fffffff, fblk = 0;
+  for (int bin = threadIdx.x; bin < d.nbins; bin += blockDim.x) {
     unsigned long long best = 0ull;
-    for (int t = 0; t < ntiles; ++t) best = p[t] > best ? p[t] : best;
-    row[r] = best;
+    int bb = 0;
+    for (int b = 0; b < d.blocks; ++b) {  // acquisition.py:129-133: an earlier block survives only if strictly larger
+      const unsigned long long* p = partial + (((long long)item * d.nbins + bin) * d.blocks + b) * ntiles;
+      unsigned long long k = 0ull;
+      for (int t = 0; t < ntiles; ++t) k = p[t] > k ? p[t] : k;
+      if (b == 0 || !(fft::key_value(best) > fft::key_value(k))) { best = k; bb = b; }
+    }
+    const float v = fft::key_value(best);
+    if (v > peak) { peak = v; fbin = bin; fblk = bb; }   // results.max(1).argmax(): first bin (bins ascend per thread)
   }
+  s_v[threadIdx.x] = peak; s_bin[threadIdx.x] = fbin; s_blk[threadIdx.x] = fblk;
   __syncthreads();
   if (threadIdx.x == 0) {
-    float peak = -1.f;
-    int fbin = 0, fblk = 0;
-    unsigned cp = 0xFFFFFFFFu;
-    for (int bin = 0; bin < d.nbins; ++bin) {
-      unsigned long long best = row[bin * d.blocks];
-      int bb = 0;
-      for (int b = 1; b < d.blocks; ++b) {  // acquisition.py:129-133: an earlier block survives only if strictly larger
-        const unsigned long long k = row[bin * d.blocks + b];
-        if (!(fft::key_value(best) > fft::key_value(k))) { best = k; bb = b; }
-      }
-      const float v = fft::key_value(best);
-      const unsigned idx = fft::key_index(best);
-      if (v > peak) { peak = v; fbin = bin; fblk = bb; cp = idx; }   // results.max(1).argmax(): first bin
-      else if (v == peak && idx < cp) cp = idx;                       // results.max(0).argmax(): first column
+    for (int t = 1; t < (int)blockDim.x; ++t)
+      if (s_v[t] > peak || (s_v[t] == peak && s_bin[t] < fbin)) { peak = s_v[t]; fbin = s_bin[t]; fblk = s_blk[t]; }
+    s_v[0] = peak; s_bin[0] = fbin; s_blk[0] = fblk;
+  }
+  __syncthreads();
+  peak = s_v[0];
+  // results.max(0).argmax(): the first column holding the global maximum, whichever bin it is in
+  unsigned cp = 0xFFFFFFFFu;
+  for (int bin = threadIdx.x; bin < d.nbins; bin += blockDim.x) {
+    unsigned long long best = 0ull;
+    for (int b = 0; b < d.blocks; ++b) {
+      const unsigned long long* p = partial + (((long long)item * d.nbins + bin) * d.blocks + b) * ntiles;
+      unsigned long long k = 0ull;
+      for (int t = 0; t < ntiles; ++t) k = p[t] > k ? p[t] : k;
+      if (b == 0 || !(fft::key_value(best) > fft::key_value(k))) best = k;
     }
+    if (fft::key_value(best) == peak && fft::key_index(best) < cp) cp = fft::key_index(best);
+  }
+  s_cp[threadIdx.x] = cp;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int t = 1; t < (int)blockDim.x; ++t) cp = s_cp[t] < cp ? s_cp[t] : cp;
     PeakSel s;
-    s.bin = fbin; s.blk = fblk; s.codePhase = (int)cp; s.peak = peak;
+    s.bin = s_bin[0]; s.blk = s_blk[0]; s.codePhase = (int)cp; s.peak = peak;
     sel[item] = s;
   }
 }
@@ -576,12 +594,13 @@ extern "C" int sgx_acquire(const int8_t* sig, int64_t rec_stride, int64_t n_samp
                            double* codePhase, double* peakMetric, int32_t* frqBin, int32_t* finePeakIndex,
                            void* cuda_stream) {
   if (sgx_device_count() <= 0) return fail(SGX_ERR_NODEV, "sgx_acquire", "no CUDA device");
+  SGX_API_GUARD();
   if (!sig || !st || !ca_table || !ca_chips || !fine_idx || !carrFreq || !codePhase || !peakMetric ||
       n_recordings <= 0 || prn_first < 0 || prn_count <= 0 || prn_first + prn_count > SGX_NUM_PRN)
     return fail(SGX_ERR_ARG, "sgx_acquire", "null pointer or PRN shard outside 0..32");
   const int n1 = st->samplesPerCode, blocks = st->acqNonCoherentBlocks, nbins = st->numFrqBins;
   const long long n = (long long)n1 * st->acqCoherentMs;
-  if (n_samples < n * blocks || n_samples < (long long)(st->fineMs + 1) * n1 || nbins * blocks > 512 || nbins <= 0)
+  if (n_samples < n * blocks || n_samples < (long long)(st->fineMs + 1) * n1 || nbins <= 0)
     return fail(SGX_ERR_ARG, "sgx_acquire", "longSignal too short (needs blocks and fineMs+1 code periods) or too many bins");
   cudaStream_t s = (cudaStream_t)cuda_stream;
   int rc = ensure_plan(st, ca_table, ca_chips, fine_idx, s);
@@ -777,6 +796,7 @@ extern "C" int sgx_acquire(const int8_t* sig, int64_t rec_stride, int64_t n_samp
 extern "C" int sgx_fft_c2c(const float* in, float* out, int32_t n, int32_t batch, int32_t inverse,
                            void* cuda_stream) {
   if (sgx_device_count() <= 0) return fail(SGX_ERR_NODEV, "sgx_fft_c2c", "no CUDA device");
+  SGX_API_GUARD();
   if (!in || !out || n < 2 || batch < 1) return fail(SGX_ERR_ARG, "sgx_fft_c2c", "bad argument");
   cudaStream_t s = (cudaStream_t)cuda_stream;
   static fft::Plan pl;   // rebuilt on every call: this is a test hook, not a hot path

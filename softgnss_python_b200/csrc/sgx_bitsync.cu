@@ -217,6 +217,7 @@ extern "C" int sgx_find_preambles(const double* i_p, int64_t stride, int32_t n_c
                                   int32_t* first_subframe, uint8_t* nav_bits, int32_t* nav_bits_valid,
                                   void* cuda_stream) {
   if (sgx_device_count() <= 0) return fail(SGX_ERR_NODEV, "sgx_find_preambles", "no CUDA device");
+  SGX_API_GUARD();
   if (!i_p || !first_subframe || n_channels < 0 || ms <= 0 || stride < ms)
     return fail(SGX_ERR_ARG, "sgx_find_preambles", "bad argument");
   if (n_channels == 0) return SGX_OK;
@@ -293,6 +294,7 @@ extern "C" int sgx_pseudoranges(const double* track_out, int32_t n_recordings, i
                                 double samples_per_code, double start_offset, double c, double* pseudoranges,
                                 void* cuda_stream) {
   if (sgx_device_count() <= 0) return fail(SGX_ERR_NODEV, "sgx_pseudoranges", "no CUDA device");
+  SGX_API_GUARD();
   if (!track_out || !ms_index || !active || !pseudoranges || n_channels < 1 || n_channels > 32 || ms <= 0 ||
       n_recordings < 0 || n_epochs < 0)
     return fail(SGX_ERR_ARG, "sgx_pseudoranges", "bad argument (1..32 channels)");

@@ -3,6 +3,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <mutex>
 
 #ifdef SGX_EMUL
 #include "cuda_emul.h"  // tools/cpu_emul: developer-only CPU single-stepping, never shipped
@@ -26,11 +27,36 @@ namespace sgx {
 
 extern char g_err[512];
 extern long long g_launches;
+extern int g_bound_device;           // the device that owns this process' plan caches and scratch buffers (-1: none yet)
+extern std::recursive_mutex g_api_mutex;
 
 inline int fail(int code, const char* what, const char* detail) {
   snprintf(g_err, sizeof(g_err), "%s: %s", what, detail ? detail : "");
   return code;
 }
+
+// Every compute entry point of the C ABI holds one of these: the plan caches and scratch buffers (FFT plans, code
+// spectra, tracking state, ...) are process-wide and live on ONE device -- the one-process-per-GPU convention of
+// bench.py / torch.distributed.  Calls are serialised, and a call made while another device is current fails with
+// SGX_ERR_ARG instead of touching memory of the wrong device.
+struct ApiGuard {
+  std::lock_guard<std::recursive_mutex> lock;
+  int rc;
+  ApiGuard() : lock(g_api_mutex), rc(0) {
+    int d = -1;
+    if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); return; }
+    if (g_bound_device < 0) g_bound_device = d;
+    else if (d != g_bound_device) {
+      char msg[160];
+      snprintf(msg, sizeof(msg), "device %d is current, but this process is bound to device %d (one process per GPU)", d,
+               g_bound_device);
+      rc = fail(SGX_ERR_ARG, "softgnss_b200", msg);
+    }
+  }
+};
+#define SGX_API_GUARD()        \
+  sgx::ApiGuard api_guard__;   \
+  if (api_guard__.rc) return api_guard__.rc
 
 #define SGX_CUDA(call)                                                          \
   do {                                                                          \

@@ -461,6 +461,7 @@ extern "C" int sgx_nav_solve(const double* abs_sample, int64_t stride, int32_t n
                              const sgx_nav_settings* st, double* raw_p, double* corrected_p, double* el, double* az,
                              double* sat_pos, double* sat_clk, uint8_t* active, double* sol, void* cuda_stream) {
   if (sgx_device_count() <= 0) return fail(SGX_ERR_NODEV, "sgx_nav_solve", "no CUDA device");
+  SGX_API_GUARD();
   if (!abs_sample || !sub_frame_start || !ready || !eph || !tow || !n_epochs || !st || !raw_p || !corrected_p || !el ||
       !az || !active || !sol || n_channels < 1 || n_channels > 32 || ms <= 0 || stride < ms || n_recordings < 0 ||
       max_epochs < 0 || !(st->nav_sol_period >= 1.0) || !(st->samples_per_code > 0))

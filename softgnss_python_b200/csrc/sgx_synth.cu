@@ -104,6 +104,7 @@ extern "C" int sgx_synth_generate(int8_t* out, int64_t rec_stride, int64_t n_sam
                                   int32_t n_recordings, const sgx_synth_spec* specs, const int8_t* bits,
                                   const int16_t* lut, const int8_t* ca_chips, void* cuda_stream) {
   if (sgx_device_count() <= 0) return fail(SGX_ERR_NODEV, "sgx_synth_generate", "no CUDA device");
+  SGX_API_GUARD();
   if (!out || !specs || !bits || !lut || !ca_chips || n_recordings <= 0 || n_samples <= 0 ||
       rec_stride < n_samples)
     return fail(SGX_ERR_ARG, "sgx_synth_generate", "bad argument");

@@ -959,6 +959,7 @@ extern "C" int sgx_track(const int8_t* rec, int64_t rec_stride, const int64_t* r
                          const sgx_settings* st, const int8_t* ca_chips, double* out,
                          int32_t* ms_done, void* cuda_stream) {
   if (sgx_device_count() <= 0) return fail(SGX_ERR_NODEV, "sgx_track", "no CUDA device");
+  SGX_API_GUARD();
   if (!rec || !rec_len || !ch || !st || !ca_chips || !out || !ms_done || n_recordings <= 0 ||
       n_channels <= 0 || st->msToProcess <= 0)
     return fail(SGX_ERR_ARG, "sgx_track", "null pointer or empty problem");

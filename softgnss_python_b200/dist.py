@@ -21,26 +21,68 @@ def _dist():
     return dist
 
 
-def gather_results(local, n_units, axis=0):
-    """All ranks contribute their shard (numpy array whose ``axis`` has the rank's unit count); every
-    rank gets the full array in unit order.  Works with any backend (tensors are moved to the
-    backend's device)."""
+def _counts(n_units, world, counts):
+    if counts is None:
+        return [shard_range(n_units, r, world) for r in range(world)]
+    bounds, lo = [], 0
+    for c in counts:
+        bounds.append((lo, lo + int(c)))
+        lo += int(c)
+    assert lo == n_units, "shard sizes do not add up to the number of units"
+    return bounds
+
+
+def gather_results(local, n_units, axis=0, counts=None):
+    """All ranks contribute their shard (array whose ``axis`` has the rank's unit count); every rank gets the full
+    array in unit order.  ``local`` may be a numpy array (result: numpy) or a torch tensor (result: tensor on the same
+    device).  A CUDA tensor under NCCL never leaves the device: the shards travel GPU -> GPU over NVLink straight
+    into their slice of the output -- one ``all_gather_into_tensor`` when the shards are equal, one broadcast per
+    rank otherwise (no padding to the widest shard, no host staging).  ``counts``: explicit units per rank
+    (default: ``shard_range``)."""
+    import torch
+    dist = _dist()
+    is_tensor = hasattr(local, "data_ptr")
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return local if is_tensor else np.asarray(local)
+    world, rank = dist.get_world_size(), dist.get_rank()
+    nccl = dist.get_backend() == "nccl"
+    bounds = _counts(n_units, world, counts)
+    if is_tensor:
+        t = local.movedim(axis, 0).contiguous()
+        if nccl and not t.is_cuda:
+            t = t.cuda()
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(np.moveaxis(np.asarray(local), axis, 0)))
+        if nccl:
+            t = t.cuda()
+    lo, hi = bounds[rank]
+    assert t.shape[0] == hi - lo, "local shard has %d units, expected %d" % (t.shape[0], hi - lo)
+    out = torch.empty((n_units,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    if len({b[1] - b[0] for b in bounds}) == 1:
+        dist.all_gather_into_tensor(out, t)
+    else:
+        for r, (a, b) in enumerate(bounds):
+            if b > a:
+                view = out[a:b]
+                if r == rank:
+                    view.copy_(t)
+                dist.broadcast(view, src=r)
+    out = out.movedim(0, axis)
+    if is_tensor:
+        return out
+    return out.cpu().numpy()
+
+
+def _all_reduce_min(value):
+    """Smallest value over the ranks (error codes are negative: any rank's failure wins)."""
     import torch
     dist = _dist()
     if not dist.is_initialized() or dist.get_world_size() == 1:
-        return np.asarray(local)
-    world, rank = dist.get_world_size(), dist.get_rank()
-    device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
-    local = np.moveaxis(np.ascontiguousarray(local), axis, 0)
-    counts = [shard_range(n_units, r, world) for r in range(world)]
-    width = max(hi - lo for lo, hi in counts)
-    pad = np.zeros((width,) + local.shape[1:], dtype=local.dtype)
-    pad[:local.shape[0]] = local
-    mine = torch.from_numpy(pad).to(device)
-    parts = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(parts, mine)
-    out = np.concatenate([p.cpu().numpy()[:hi - lo] for p, (lo, hi) in zip(parts, counts)], axis=0)
-    return np.moveaxis(out, 0, axis)
+        return int(value)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.tensor([int(value)], dtype=torch.int64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return int(t.item())
 
 
 def acquire_sharded(signals, settings, stream=0):
@@ -55,27 +97,45 @@ def acquire_sharded(signals, settings, stream=0):
     res = acquire_batch(signals, settings, prn_first=lo, prn_count=hi - lo, stream=stream) if hi > lo else \
         dict(carrFreq=np.zeros((signals.shape[0], 0)), codePhase=np.zeros((signals.shape[0], 0)),
              peakMetric=np.zeros((signals.shape[0], 0)))
-    return {k: gather_results(v, nsat, axis=1) for k, v in res.items()}
+    # one gather for the three result arrays: [3][R][prn]
+    packed = np.stack([res["carrFreq"], res["codePhase"], res["peakMetric"]])
+    full = gather_results(packed, nsat, axis=2)
+    return dict(carrFreq=full[0], codePhase=full[1], peakMetric=full[2])
 
 
-def track_sharded(recordings, rec_len, channel_sets, settings, stream=0):
+def track_sharded(recordings, rec_len, channel_sets, settings, stream=0, gather=True):
     """Tracking of this rank's recordings (the caller passes only the local shard: recordings live on
-    the GPU that tracks them); returns the gathered ``out [R_total, C, 13, ms]`` and ``ms_done``."""
+    the GPU that tracks them).  Returns ``(rc, out, ms_done)`` with ``rc`` the most severe status of ANY rank (so a
+    short recording on one rank is seen by all).  ``gather=True``: ``out [R_total, C, 13, ms]`` and ``ms_done`` of
+    all ranks in rank order; with device-resident recordings the result buffers stay on the GPUs and are gathered
+    GPU to GPU.  ``gather=False``: every rank keeps (and may copy to its own host) its shard only -- SURVEY.md
+    section 8(e) allows either.  Rows of idle (PRN 0) or stopped channels are zero, not uninitialised."""
     from .tracking import track_batch
+    from ._native import TRACK_FIELDS
     dist = _dist()
     world = dist.get_world_size() if dist.is_initialized() else 1
-    rc, out, done = track_batch(recordings, rec_len, channel_sets, settings, stream=stream)
-    if hasattr(out, "cpu"):
-        out = out.cpu().numpy()
+    on_device = hasattr(recordings, "data_ptr") and recordings.is_cuda
+    ms = int(settings.msToProcess)
+    shape = (len(channel_sets), int(settings.numberOfChannels), len(TRACK_FIELDS), ms)
+    if on_device:
+        import torch
+        out = torch.zeros(shape, dtype=torch.float64, device=recordings.device)
+    else:
+        out = np.zeros(shape, dtype=np.float64)
+    rc, out, done = track_batch(recordings, rec_len, channel_sets, settings, out=out, stream=stream)
     if world == 1:
         return rc, out, done
+    rc = _all_reduce_min(rc)
+    if not gather:
+        return rc, out, done
     import torch
-    n_local = torch.tensor([len(channel_sets)])
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    n_local = torch.tensor([len(channel_sets)], dtype=torch.int64, device=dev)
     counts = [torch.zeros_like(n_local) for _ in range(world)]
-    dist.all_gather(counts, n_local.to("cuda") if dist.get_backend() == "nccl" else n_local)
-    total = int(sum(int(c.item()) for c in counts))
-    assert all(int(c.item()) == len(channel_sets) for c in counts), "equal shards expected"
-    return rc, gather_results(out, total, axis=0), gather_results(done, total, axis=0)
+    dist.all_gather(counts, n_local)
+    counts = [int(c.item()) for c in counts]
+    total = sum(counts)
+    return rc, gather_results(out, total, axis=0, counts=counts), gather_results(done, total, axis=0, counts=counts)
 
 
 def gather_epochs(local, n_units):

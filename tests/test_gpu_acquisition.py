@@ -134,4 +134,4 @@ def test_end_to_end_acquire_prerun_track(recordings):
     t = TrackingResult(a)
     t.track(data)
     got = {f: np.stack([np.asarray(x, dtype=np.float64) for x in t.results[f]]) for f in TRACK_FIELDS}
-    compare_tracking(got, {f: g["trk_" + f] for f in TRACK_FIELDS}, "e2e")
+    compare_tracking(got, {f: g["trk_" + f] for f in TRACK_FIELDS}, "e2e", strict=True)

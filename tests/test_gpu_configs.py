@@ -49,7 +49,7 @@ def test_sampling_rate_sweep_acquire_and_track(fs, f_if):
     assert rc == 0 and (done == 12).all()
     got_t = {f: out[0, :, i, :] for i, f in enumerate(TRACK_FIELDS)}
     ref_t = {f: np.stack([r[2][f] for r in recs]) for f in TRACK_FIELDS}
-    compare_tracking(got_t, ref_t, "fs=%g" % fs)
+    compare_tracking(got_t, ref_t, "fs=%g" % fs, strict=True)       # every rate of the sweep runs the exact correlator
 
 
 @pytest.mark.parametrize("coh,blocks,step", [(2, 3, 250.0), (1, 4, 500.0), (5, 2, 100.0)])

@@ -120,7 +120,7 @@ def test_fresh_seed_against_oracle(native):
     res, _ = tracking(data, ch, s)
     got = _fields(res)
     ref = {f: np.stack([r[2][f] for r in recs]) for f in native.TRACK_FIELDS}
-    compare_tracking(got, ref, "fresh")
+    compare_tracking(got, ref, "fresh", strict=True)               # default settings: exact correlator variant
 
 
 def test_batch_device_resident_equals_single(native, recordings):
