@@ -116,8 +116,14 @@ class ClockSampler(object):
 
 
 # ------------------------------------------------------------------------------------------ workloads
-def make_specs(first_seed, count):
-    from softgnss_python_b200 import synth
+def make_specs(first_seed, count, lnav=False):
+    """Synthetic 8-satellite recordings.  lnav=True: valid LNAV frames, Kepler geometry and range-consistent delays
+    (navsynth.build_scenario) -- the tracking workload, so that the preamble search and the navigation chain that
+    follow it in the bench find what postNavigation needs; lnav=False: random Doppler / code phase / data bits (the
+    11 ms acquisition batches)."""
+    from softgnss_python_b200 import navsynth, synth
+    if lnav:
+        return [navsynth.build_scenario(seed=first_seed + r)[0] for r in range(count)]
     return [synth.RecordingSpec(synth.default_constellation(first_seed + r, CHANNELS), seed=first_seed + r)
             for r in range(count)]
 
@@ -154,7 +160,7 @@ def run_gpu(args, rank, world):
     recs, ms = args.recordings, args.ms
     settings = Settings(msToProcess=float(ms))
     pod = to_pod(settings)
-    specs = make_specs(2000 + rank * recs, recs)
+    specs = make_specs(2000 + rank * recs, recs, lnav=True)
     n = (ms + 2) * N_CODE
     stride = (n + 15) // 16 * 16
     dev = torch.empty((recs, stride), dtype=torch.int8, device="cuda")
@@ -219,6 +225,20 @@ def run_gpu(args, rank, world):
             del dev
             torch.cuda.empty_cache()
             hin, hres = host.numpy(), hout.numpy()
+            # ceiling of this box: every rank copies pinned host memory to its GPU at the same time (bare copies)
+            probe = torch.empty(min(1 << 30, host.numel()), dtype=torch.int8, device="cuda")
+            barrier()
+            h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            h0.record()
+            for _ in range(3):
+                probe.copy_(host.view(-1)[:probe.numel()], non_blocking=True)
+            h1.record()
+            barrier()
+            th = torch.tensor([h0.elapsed_time(h1)], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(th, op=dist.ReduceOp.MAX)
+            h2d_gbs = 3 * probe.numel() / (float(th.item()) / 1e3) / 1e9      # per GPU, slowest rank
+            del probe
             echans = _native.make_channels(*channel_truth(specs[:erecs]))
             eunits = erecs * CHANNELS * ms
 
@@ -243,6 +263,11 @@ def run_gpu(args, rank, world):
             e2e = {"value": world * eunits / (e2e_ms / 1e3), "unit": "channel-ms/s",
                    "h2d_bytes_per_step": int(erecs * n), "d2h_bytes_per_step": int(hres.nbytes),
                    "ms_per_step": e2e_ms, "steps": ksteps, "recordings_per_gpu": erecs,
+                   "h2d_ceiling_gbs_per_gpu": h2d_gbs, "h2d_ceiling_gbs_all_gpus": h2d_gbs * world,
+                   "h2d_achieved_gbs_per_gpu": erecs * n / (e2e_ms / 1e3) / 1e9,
+                   "frac_of_h2d_ceiling": (erecs * n / (e2e_ms / 1e3) / 1e9) / h2d_gbs,
+                   "h2d_note": "ceiling = concurrent bare cudaMemcpyAsync of 1 GiB pinned buffers on all ranks (slowest "
+                               "rank); the e2e step cannot be faster than its input bytes / this rate",
                    "path": "sgx_track with host pointers: chunked H2D on a copy stream overlapped with the kernel, "
                            "results D2H at the end"}
             del host, hout
@@ -290,6 +315,18 @@ def run_gpu(args, rank, world):
             dist.all_reduce(tb, op=dist.ReduceOp.MAX)
         ae_ms = float(tb.item()) / args.steps
         truth = sum(len(s.sats) for s in aspecs)
+        # config 1 itself: ONE 11 ms recording (latency of acquisition(longSignal, settings) with the signal in HBM)
+        for _ in range(2):
+            acquire_batch(adev[:1], aset, stream=stream)
+        barrier()
+        a0.record()
+        for _ in range(args.steps):
+            acquire_batch(adev[:1], aset, stream=stream)
+        a1.record()
+        barrier()
+        a1_ms = a0.elapsed_time(a1) / args.steps
+        fp32_peak = L.fp32_peak(stream)                       # FFMA burn on this GPU, TFLOP/s
+        acq_tflops = cells * FLOP_PER_CELL / (a_ms / 1e3) / 1e12
         acq = {"metric": "acq search cells/s", "value": world * cells / (a_ms / 1e3), "unit": "cells/s",
                "ms_per_step": a_ms, "gpu_launches": int(alaunch),
                "config": {"workload": "config 1 settings (32 PRN x 29 bins x 38192 code phases + fine search), "
@@ -297,11 +334,25 @@ def run_gpu(args, rank, world):
                           "detected": int((res["carrFreq"] > 0).sum()), "present": truth},
                "e2e": {"value": world * cells / (ae_ms / 1e3), "unit": "cells/s",
                        "h2d_bytes_per_step": int(areq * an), "d2h_bytes_per_step": int(areq * 32 * 3 * 8)},
+               "single_recording": {"ms": a1_ms, "cells_per_s": 32 * 29 * N_CODE / (a1_ms / 1e3),
+                                    "note": "config 1 as written: one 11 ms recording, 32 PRN x 29 bins + fine search"},
                "roofline": {"bound": "fp32 (CUDA-core FFT; not HBM: 0.3 B/cell)",
-                            "achieved": world * cells * FLOP_PER_CELL / (a_ms / 1e3) / 1e12 / world,
-                            "peak": 74.5, "unit": "TFLOP/s",
-                            "frac": cells * FLOP_PER_CELL / (a_ms / 1e3) / 1e12 / 74.5,
-                            "note": "reference-formulation FLOPs (330/cell); peak = nominal 148 SM x 128 x 2 x 1.965 GHz"}}
+                            "achieved": acq_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
+                            "frac": acq_tflops / fp32_peak, "frac_of_nominal_74.5": acq_tflops / 74.5,
+                            "note": "reference-formulation FLOPs (330/cell, SURVEY.md 8(d)); peak = FP32 FMA burn "
+                                    "measured on this GPU in this run (sgx_fp32_peak; nominal 74.5)"}}
+        if rank == 0 and not args.no_cpu:
+            from oracle import gnss_oracle as orc
+            one = adev[0].cpu().numpy()
+            t0 = time.perf_counter()
+            oref = orc.acquire(one, aset)
+            dt = time.perf_counter() - t0
+            acq["cpu_baseline"] = {"value": 32 * 29 * N_CODE / dt, "unit": "cells/s", "cores": 1, "kind": "port",
+                                   "sample": "one of the %d recordings in full (32 PRN x 29 bins + fine search), "
+                                             "oracle/gnss_oracle.py acquire (numpy restatement of acquisition.py:49-204 with "
+                                             "the carrier wipe-off hoisted out of the PRN loop), %.1f s" % (areq, dt)}
+            assert np.array_equal(oref["carrFreq"] > 0, res["carrFreq"][0] > 0), "acquisition differs from the oracle"
+            assert np.array_equal(oref["codePhase"], res["codePhase"][0])
 
     # ---- tertiary: preamble search / bit summation on the device-resident tracking result (8(f) row 3) ----
     bsync = None
@@ -347,28 +398,21 @@ def run_gpu(args, rank, world):
                                                % (CHANNELS, ms)}
             assert np.array_equal(of, first[:CHANNELS]), "bit sync differs from the oracle"
 
-    # ---- quaternary: measurement loop of postNavigate on the device (8(f) row 4) --------------------------
+    # ---- quaternary: preamble search -> ephemeris decoding -> measurement loop on the tracking result (8(f) rows 3-4) ----
     navb = None
-    if not args.no_acq:
+    if not args.no_acq and ms >= 36000:
         from softgnss_python_b200 import postnav
-        from tests.cases import NAV_MS, load_nav_cases, nav_abs_sample     # committed input vectors (not the oracle)
-        from tests import nav_util
-        ncases = load_nav_cases()
-        ns = nav_util.settings_for(ncases[0], CHANNELS, NAV_MS)
-        nrec = recs
-        n_in = [nav_util.case_inputs(ncases[r % len(ncases)]) for r in range(nrec)]
-        n_abs = torch.from_numpy(np.stack([nav_abs_sample(ncases[r % len(ncases)]["coef"]) + 38192.0 * r
-                                           for r in range(nrec)])).cuda()
-        n_args = (n_abs, np.stack([x[0] for x in n_in]), np.stack([x[1] for x in n_in]), np.stack([x[2] for x in n_in]),
-                  [ncases[r % len(ncases)]["tow"] for r in range(nrec)], ns)
+        nset = Settings(msToProcess=float(ms))
+        nset.useTropCorr = False                       # the synthetic geometry has no troposphere
+        prn_arr = np.array(channel_truth(specs)[0], dtype=np.int64).reshape(recs, CHANNELS)
         for _ in range(args.warmup):
-            postnav.nav_solve_batch(*n_args, stream=stream)
+            postnav.post_navigate_batch(out, prn_arr, nset, stream=stream)
         barrier()
         q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ql0 = L.launches()
         q0.record()
         for _ in range(args.steps):
-            nout = postnav.nav_solve_batch(*n_args, stream=stream)
+            nout = postnav.post_navigate_batch(out, prn_arr, nset, stream=stream)
         q1.record()
         barrier()
         tq = torch.tensor([q0.elapsed_time(q1)], dtype=torch.float64, device="cuda")
@@ -376,31 +420,125 @@ def run_gpu(args, rank, world):
             dist.all_reduce(tq, op=dist.ReduceOp.MAX)
         q_ms = float(tq.item()) / args.steps
         n_fix = int(nout["n_epochs"].sum())
+        from softgnss_python_b200 import navsynth
+        rx = navsynth.build_scenario(seed=2000 + rank * recs)[1]["rx"]
+        sol0 = nout["sol"][0, :int(nout["n_epochs"][0])]
+        err0 = np.sqrt(((sol0[:, :3] - rx) ** 2).sum(1))
         navb = {"metric": "navigation epochs/s", "value": world * n_fix / (q_ms / 1e3), "unit": "epochs/s",
                 "ms_per_step": q_ms, "gpu_launches": int(L.launches() - ql0),
-                "config": {"workload": "%d recordings x %d channels x %d measurement epochs per GPU: pseudoranges, satpos, "
-                                       "7-iteration least-squares fix with tropospheric correction, DOP, cart2geo; "
-                                       "absoluteSample resident on the device, results copied to the host inside the "
-                                       "timed region" % (nrec, CHANNELS, int(nout["n_epochs"][0])),
-                           "epochs_with_fix": int(np.isfinite(nout["sol"][:, :, 0]).sum())},
+                "config": {"workload": "postNavigate chain on the tracking result of the step above (device resident, %d "
+                                       "recordings x %d channels per GPU): preamble search + 1501 nav bits per channel "
+                                       "(device), ephemeris decoding (host bit slicing), pseudoranges / satpos / 7-iteration "
+                                       "least-squares fix / DOP / cart2geo for %d measurement epochs per recording (device); "
+                                       "solutions copied to the host inside the timed region"
+                                       % (recs, CHANNELS, int(nout["n_epochs"][0])),
+                           "epochs_with_fix": int(np.isfinite(nout["sol"][:, :, 0]).sum()),
+                           "recordings_with_solution": int((nout["n_epochs"] > 0).sum()),
+                           "median_3d_error_to_true_antenna_m": float(np.median(err0))},
                 "roofline": {"bound": "latency (one warp per recording, epochs sequential through the elevation mask; "
                                       "float64 dependency chain)", "frac": None}}
         if rank == 0 and not args.no_cpu:
             from oracle import gnss_oracle as orc
-            c0_ = ncases[0]
+            trk0 = out[0].cpu().numpy()
             t0 = time.perf_counter()
-            o = orc.nav_solve(nav_abs_sample(c0_["coef"]), c0_["prn"], c0_["sub_frame_start"], c0_["ready"], c0_["eph"],
-                              c0_["tow"], float(NAV_MS), 38192, elevation_mask=ns.elevationMask, use_trop_corr=ns.useTropCorr)
+            of, oa = orc.find_preambles([trk0[c, 3] for c in range(CHANNELS)])
+            eph, tow, ready = [None] * 32, None, []
+            for c in oa:
+                if of[c] + 30000 > ms:
+                    continue
+                b = orc.nav_bits(trk0[c, 3], int(of[c]))
+                e, tow = orc.ephemeris(b[1:], b[0])
+                eph[int(prn_arr[0, c]) - 1] = e
+                if e["IODC"] is not None and e["IODE_sf2"] is not None and e["IODE_sf3"] is not None:
+                    ready.append(c)
+            o = orc.nav_solve([trk0[c, 0] for c in range(CHANNELS)], prn_arr[0], of, ready, eph, tow, float(ms), N_CODE,
+                              elevation_mask=nset.elevationMask, use_trop_corr=nset.useTropCorr)
             dt = time.perf_counter() - t0
             navb["cpu_baseline"] = {"value": o["n_epochs"] / dt, "unit": "epochs/s", "cores": 1, "kind": "port",
-                                    "sample": "1 recording x 8 channels x %d epochs, oracle/gnss_oracle.py nav_solve "
-                                              "(bit-identical to the reference's loop)" % o["n_epochs"]}
-            nav_util.compare_nav(nout, 0, o, "bench nav solve")
+                                    "sample": "the same chain for recording 0 (8 channels x %d ms, %d epochs) with "
+                                              "oracle/gnss_oracle.py: find_preambles, nav_bits, ephemeris, nav_solve"
+                                              % (ms, o["n_epochs"])}
+            assert o["n_epochs"] == int(nout["n_epochs"][0])
+            assert np.abs(sol0[:, 0] - o["X"]).max() <= 1e-5 and np.abs(sol0[:, 2] - o["Z"]).max() <= 1e-5, "nav chain differs"
+
+    # ---- config 3 (weak-signal acquisition, 141 bins): 10 ms coherent and 10 x 1 ms blocks, split by PRN over the ranks ----
+    c3 = None
+    if not args.no_acq and args.c3_recordings > 0:
+        from softgnss_python_b200 import dist as sd
+        c3 = {}
+        c3n = args.c3_recordings
+        c3specs = make_specs(1000, c3n)                      # every rank holds the same recordings: the split is by PRN
+        c3dev = torch.empty((c3n, 11 * N_CODE), dtype=torch.int8, device="cuda")
+        c3sp, c3bits = _native.make_synth_specs(c3specs)
+        L.synth(c3dev, 11 * N_CODE, 11 * N_CODE, 0, c3sp, c3bits, lut, chips, stream)
+        for name, ext in (("coherent_10ms", dict(acqCoherentMs=10, acqNonCoherentBlocks=1, acqDopplerStep=100.0)),
+                          ("blocks_10x1ms", dict(acqCoherentMs=1, acqNonCoherentBlocks=10, acqDopplerStep=100.0))):
+            cs = Settings(**ext)
+            sd.acquire_sharded(c3dev, cs, stream=stream)
+            barrier()
+            z0, z1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            z0.record()
+            r3 = sd.acquire_sharded(c3dev, cs, stream=stream)
+            z1.record()
+            barrier()
+            tz = torch.tensor([z0.elapsed_time(z1)], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tz, op=dist.ReduceOp.MAX)
+            cells3 = c3n * 32 * 141 * N_CODE
+            c3[name] = {"value": cells3 / (float(tz.item()) / 1e3), "unit": "cells/s", "ms_per_step": float(tz.item()),
+                        "recordings": c3n, "bins": 141, "prn_per_rank": 32 // world,
+                        "detected": int((r3["carrFreq"] > 0).sum())}
+        c3["note"] = ("BASELINE config 3 settings on %d recordings at 45 dB-Hz, 32 PRNs split by PRN over the ranks "
+                      "(dist.acquire_sharded, results gathered over NCCL); parity at 30-43 dB-Hz: tests/test_gpu_config3.py" % c3n)
+        del c3dev
+
+    # ---- collectives (world > 1): PRN-split acquisition of one batch and the result gathers, timed separately ----------
+    coll = None
+    if world > 1 and not args.no_acq:
+        from softgnss_python_b200 import dist as sd
+        coll = {}
+        sd.acquire_sharded(adev, aset, stream=stream)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        rs = sd.acquire_sharded(adev, aset, stream=stream)
+        g1.record()
+        barrier()
+        tg = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        coll["acquire_sharded_by_prn"] = {"ms": float(tg.item()), "cells_per_s": areq * 32 * 29 * N_CODE / (float(tg.item()) / 1e3),
+                                           "note": "the SAME %d recordings on every rank, 32/%d PRNs each, gather included"
+                                                   % (areq, world)}
+        packed = torch.zeros((3, areq, 32 // world), dtype=torch.float64, device="cuda")
+        sd.gather_results(packed, 32 // world * world, axis=2)
+        barrier()
+        g0.record()
+        for _ in range(10):
+            sd.gather_results(packed, 32 // world * world, axis=2)
+        g1.record()
+        barrier()
+        coll["acq_results_gather"] = {"ms": g0.elapsed_time(g1) / 10, "bytes_per_rank": int(packed.numel() * 8),
+                                      "note": "latency only (SURVEY.md 8(e))"}
+        sd.gather_results(out[:1], world, axis=0)
+        barrier()
+        g0.record()
+        full = sd.gather_results(out, world * recs, axis=0)          # trackResults of all ranks, GPU to GPU
+        g1.record()
+        barrier()
+        tg = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        nbytes = int(out.numel() * 8)
+        coll["track_results_gather"] = {"ms": float(tg.item()), "bytes_per_rank": nbytes, "total_bytes": nbytes * world,
+                                         "bus_gbs_per_gpu": nbytes * (world - 1) / (float(tg.item()) / 1e3) / 1e9,
+                                         "note": "all_gather_into_tensor of the device-resident [R][C][13][ms] float64 results "
+                                                 "(NCCL over NVLink); bus bandwidth = bytes received per GPU / time"}
+        assert torch.equal(full[rank * recs:(rank + 1) * recs], out)
+        del full
 
     ck = clocks.stop(c0, c1) if clocks else None
     if world > 1:
         counts = [None] * world
-        dist.all_gather_object(counts, int(done.sum()))          # the only collective: gather of results
+        dist.all_gather_object(counts, int(done.sum()))
         dist.destroy_process_group()
     if rank != 0:
         return
@@ -431,6 +569,14 @@ def run_gpu(args, rank, world):
         "secondary": acq,
         "tertiary": bsync,
         "quaternary": navb,
+        "config3": c3,
+        "collectives": coll,
+        # the acquisition half of BASELINE.json's metric, lifted so that per-N records keep it
+        "acq_value": acq["value"] if acq else None,
+        "acq_unit": "cells/s",
+        "acq_ms_per_step": acq["ms_per_step"] if acq else None,
+        "acq_roofline_frac": acq["roofline"]["frac"] if acq else None,
+        "acq_e2e_value": acq["e2e"]["value"] if acq else None,
     }
     if not args.no_cpu:
         line["cpu_baseline"] = cpu_track_baseline(TRACK_CPU_MS, 1)
@@ -447,7 +593,7 @@ def _cpu_prepare(ms):
         return
     from softgnss_python_b200 import synth
     from softgnss_python_b200.settings import Settings
-    spec = make_specs(2000, 1)[0]
+    spec = make_specs(2000, 1, lnav=True)[0]
     _CPU.update(ms=ms, data=synth.generate_cpu(spec, (ms + 2) * N_CODE), truth=channel_truth([spec]),
                 settings=Settings(msToProcess=float(ms)))
 
@@ -481,6 +627,31 @@ def cpu_track_baseline(ms, procs):
                       "(numpy restatement of the reference loop; numpy %s)" % (n_ch, ms, np.__version__)}
 
 
+def _cpu_acq_one(seed):
+    from oracle import gnss_oracle as orc
+    from softgnss_python_b200 import synth
+    from softgnss_python_b200.settings import Settings
+    spec = make_specs(seed, 1)[0]
+    data = synth.generate_cpu(spec, 11 * N_CODE)
+    t = time.perf_counter()
+    r = orc.acquire(data, Settings())
+    return time.perf_counter() - t, int((r["carrFreq"] > 0).sum())
+
+
+def cpu_acq_baseline(procs):
+    """Oracle acquisition (numpy restatement of acquisition.py:49-204), one full config-1 recording per process."""
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(procs) as pool:
+        t = time.perf_counter()
+        res = pool.map(_cpu_acq_one, [1000 + i for i in range(procs)], chunksize=1)
+        dt = time.perf_counter() - t
+    return {"value": procs * 32 * 29 * N_CODE / dt, "unit": "cells/s", "cores": procs, "kind": "port",
+            "ms_per_step": dt * 1e3, "detected": int(sum(x[1] for x in res)),
+            "sample": "%d config-1 recordings (11 ms, 32 PRN x 29 bins + fine search), one per process, "
+                      "oracle/gnss_oracle.py acquire; recording generation excluded from the per-process time but the "
+                      "wall clock of the pool is what is reported" % procs}
+
+
 def run_reference(args, rank):
     """--impl reference: the reference's CPU algorithm (oracle port) on all host cores."""
     if rank != 0:
@@ -503,6 +674,14 @@ def run_reference(args, rank):
                                    "runs a bounded sample of it" % (REC_PER_GPU, CHANNELS, MS)},
             "cpu_baseline": base,
             "e2e": {"value": v, "unit": "channel-ms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if not args.no_acq:
+        a = cpu_acq_baseline(procs)
+        line["secondary"] = {"metric": "acq search cells/s", "value": a["value"], "unit": "cells/s",
+                             "ms_per_step": a["ms_per_step"], "cpu_baseline": a,
+                             "config": {"workload": "config 1 settings, one 11 ms recording per host core"}}
+        line["acq_value"] = a["value"]
+        line["acq_unit"] = "cells/s"
+        line["acq_ms_per_step"] = a["ms_per_step"]
     emit(line)
 
 
@@ -515,6 +694,7 @@ def main():
     ap.add_argument("--recordings", type=int, default=REC_PER_GPU, help="recordings per GPU")
     ap.add_argument("--ms", type=int, default=MS)
     ap.add_argument("--acq-recordings", type=int, default=ACQ_REC_PER_GPU)
+    ap.add_argument("--c3-recordings", type=int, default=2, help="recordings of the config-3 leg (0 = skip)")
     ap.add_argument("--ref-ms", type=int, default=400, help="code periods per channel per CPU step")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-acq", action="store_true")
