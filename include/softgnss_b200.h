@@ -130,6 +130,20 @@ int sgx_track(const int8_t* rec, int64_t rec_stride, const int64_t* rec_len, int
               const sgx_channel* ch, int32_t n_channels, const sgx_settings* st,
               const int8_t* ca_chips, double* out, int32_t* ms_done, void* cuda_stream);
 
+/* The same for ONE recording that lives in a file: replaces fid.seek / np.fromfile(fid, dataType, blksize) of
+ * tracking.py:107, :154 and the dataType / skipNumberOfBytes handling of initialize.py:102, :466-481 (SURVEY.md
+ * section 8(f) row 2).  The file is read with pread() in chunks of `chunk_samples` (0: 1024 code periods) into two
+ * pinned staging buffers and copied to HBM while the kernel tracks the periods already resident; only the window
+ * tracking can touch is read (first sample of the earliest channel ... msToProcess code periods after the latest),
+ * reported in window[0..1] when non-NULL.
+ *   sample_bytes  1: int8 (the reference's format), 2: little-endian int16 whose values fit int8 (SGX_ERR_ARG
+ *                 otherwise).  For int16 positions count SAMPLES: the start is skipNumberOfBytes/2 + codePhase and
+ *                 absoluteSample is a sample index (the reference mixes bytes and samples for multi-byte types).
+ * Results as sgx_track with n_recordings = 1; a file that ends early gives SGX_ERR_SHORT. */
+int sgx_track_file(const char* path, int32_t sample_bytes, const sgx_channel* ch, int32_t n_channels,
+                   const sgx_settings* st, const int8_t* ca_chips, double* out, int32_t* ms_done,
+                   int64_t chunk_samples, int64_t* window, void* cuda_stream);
+
 /* Synthetic int8 IF recordings, bit-identical to synth.generate_cpu.
  *   out   int8 [n_recordings][rec_stride] (host or device), samples start .. start+n_samples-1
  *   bits  host int8 [n_recordings][SGX_SYNTH_MAX_SATS][n_bits] nav bits (+-1)

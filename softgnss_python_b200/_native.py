@@ -19,7 +19,7 @@ TRACK_FIELDS = ("absoluteSample", "codeFreq", "carrFreq", "I_P", "I_E", "I_L", "
 SGX_ERR_SHORT = -3
 
 EXPORTS = ("sgx_abi_version", "sgx_last_error", "sgx_device_count", "sgx_set_device", "sgx_fp32_peak",
-           "sgx_kernel_launch_count", "sgx_acquire", "sgx_track", "sgx_synth_generate", "sgx_fft_c2c",
+           "sgx_kernel_launch_count", "sgx_acquire", "sgx_track", "sgx_track_file", "sgx_synth_generate", "sgx_fft_c2c",
            "sgx_find_preambles", "sgx_pseudoranges", "sgx_nav_solve")
 
 
@@ -83,6 +83,7 @@ class Lib(object):
         d.sgx_set_device.argtypes = [ctypes.c_int]
         d.sgx_kernel_launch_count.restype = i64
         d.sgx_track.argtypes = [vp, i64, vp, i32, vp, i32, ctypes.POINTER(SgxSettings), vp, vp, vp, vp]
+        d.sgx_track_file.argtypes = [ctypes.c_char_p, i32, vp, i32, ctypes.POINTER(SgxSettings), vp, vp, vp, i64, vp, vp]
         d.sgx_synth_generate.argtypes = [vp, i64, i64, i64, i32, vp, vp, vp, vp, vp]
         if hasattr(d, "sgx_acquire"):
             d.sgx_acquire.argtypes = [vp, i64, i64, i32, ctypes.POINTER(SgxSettings), vp, vp, vp, i32, i32,
@@ -119,6 +120,18 @@ class Lib(object):
                                 ctypes.byref(pod), _ptr(ca_chips), _ptr(out), _ptr(ms_done),
                                 ctypes.c_void_p(stream))
         return rc, ms_done
+
+    def track_file(self, path, sample_bytes, channels, pod, ca_chips, out, chunk_samples=0, stream=0):
+        """One recording streamed from a file (pread -> pinned double buffer -> HBM).  Returns
+        (rc, ms_done[1, C], (first sample, samples) of the window that was read)."""
+        self.require_device()
+        c = len(channels)
+        ms_done = np.zeros((1, c), dtype=np.int32)
+        window = np.zeros(2, dtype=np.int64)
+        rc = self.dll.sgx_track_file(os.fsencode(path), int(sample_bytes), _ptr(channels), c, ctypes.byref(pod),
+                                     _ptr(ca_chips), _ptr(out), _ptr(ms_done), int(chunk_samples), _ptr(window),
+                                     ctypes.c_void_p(stream))
+        return rc, ms_done, (int(window[0]), int(window[1]))
 
     def fft(self, x, inverse=False, stream=0, persistent=False):
         """Unnormalised FFT of the rows of complex64 x through the acquisition FFT engine (test hook);

@@ -27,6 +27,9 @@
 //  * thread 0 then runs T8/T9/T5/T3 in float64 with separately rounded operations (compiled with
 //    -fmad=false) exactly in the reference's order and publishes the next period's parameters.
 #include <vector>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include "sgx_common.cuh"
 
 namespace sgx {
@@ -52,6 +55,7 @@ struct TrackArgs {
   long long* prof;      // optional [R*C][4] cycle counters (SGX_TRK_PROF=1): correlate, reduce+barrier, bookkeeping, barrier
   int win;              // bytes per staging buffer, multiple of 16
   long long skip;
+  long long abs_base;   // sample index of rec[0] in the file (streamed windows start at the first byte that is needed)
   double fs, codeFreqBasis, codeLength, spc;
   double c1code, c2code, c1carr, c2carr;  // tau2/tau1 and PDI/tau1 (tracking.py:225-227, 241-243)
 };
@@ -887,7 +891,7 @@ __global__ void __launch_bounds__(NT, 2) track_kernel(TrackArgs a) {
       if (k + 1 < a.ms) prepare_code(a, cst, rec_len, prm);
       double* o = a.out + (long long)cid * SGX_TRACK_FIELDS * a.ms + k;   // record (tracking.py:255-275)
       const long long m = a.ms;
-      o[0 * m] = (double)cst.pos;  // fid.tell() after the read
+      o[0 * m] = (double)(cst.pos + a.abs_base);  // fid.tell() after the read
       o[1 * m] = cst.codeFreq;
       o[4 * m] = I_E; o[5 * m] = I_L; o[6 * m] = Q_E; o[8 * m] = Q_L;
       o[9 * m] = codeError; o[10 * m] = codeNco;
@@ -942,6 +946,20 @@ struct TrackScratch {
   DevBuf rec, len, ch, chips, out, done, status, state, prof;
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev[2] = {nullptr, nullptr};
+  // file ingest: two pinned staging buffers, filled by pread() while the other one is on its way to the device
+  int8_t* pin[2] = {nullptr, nullptr};
+  size_t pin_cap = 0;
+  cudaEvent_t pin_ev[2] = {nullptr, nullptr};
+};
+
+// A recording that lives in a file (sgx_track_file): samples [base, base + len) are what tracking can touch.
+struct FileSrc {
+  int fd;
+  int sample_bytes;      // 1: int8 (the reference's format), 2: int16 little endian, values must fit int8
+  long long base;        // first sample of the window, multiple of 16
+  long long len;         // samples in the window
+  long long chunk;       // samples per staging buffer
+  int bad_value;         // set when an int16 sample does not fit int8
 };
 static TrackScratch g_trk;
 
@@ -954,13 +972,11 @@ static bool use_bulk() {
 
 using namespace sgx;
 
-extern "C" int sgx_track(const int8_t* rec, int64_t rec_stride, const int64_t* rec_len,
-                         int32_t n_recordings, const sgx_channel* ch, int32_t n_channels,
-                         const sgx_settings* st, const int8_t* ca_chips, double* out,
-                         int32_t* ms_done, void* cuda_stream) {
-  if (sgx_device_count() <= 0) return fail(SGX_ERR_NODEV, "sgx_track", "no CUDA device");
-  SGX_API_GUARD();
-  if (!rec || !rec_len || !ch || !st || !ca_chips || !out || !ms_done || n_recordings <= 0 ||
+static int track_core(const int8_t* rec, int64_t rec_stride, const int64_t* rec_len,
+                      int32_t n_recordings, const sgx_channel* ch, int32_t n_channels,
+                      const sgx_settings* st, const int8_t* ca_chips, double* out,
+                      int32_t* ms_done, void* cuda_stream, sgx::FileSrc* file) {
+  if ((!rec && !file) || !rec_len || !ch || !st || !ca_chips || !out || !ms_done || n_recordings <= 0 ||
       n_channels <= 0 || st->msToProcess <= 0)
     return fail(SGX_ERR_ARG, "sgx_track", "null pointer or empty problem");
   const int nch = n_recordings * n_channels;
@@ -974,7 +990,7 @@ extern "C" int sgx_track(const int8_t* rec, int64_t rec_stride, const int64_t* r
   long long stride = rec_stride;
   long long max_len = 0;
   for (int r = 0; r < n_recordings; ++r) max_len = rec_len[r] > max_len ? rec_len[r] : max_len;
-  const bool host_input = !is_device_ptr(rec);
+  const bool host_input = file || !is_device_ptr(rec);
   if (host_input) {  // host recording: it is streamed into HBM in chunks while tracking runs (np.fromfile replacement)
     stride = (max_len + 15) & ~15LL;
     if (g_trk.rec.reserve((size_t)stride * n_recordings + 16)) return fail(SGX_ERR_CUDA, "cudaMalloc", "recording");
@@ -1018,7 +1034,8 @@ extern "C" int sgx_track(const int8_t* rec, int64_t rec_stride, const int64_t* r
     a.prof = g_trk.prof.as<long long>();
   }
   a.win = win;
-  a.skip = st->skipNumberOfBytes;
+  a.skip = file ? st->skipNumberOfBytes / file->sample_bytes - file->base : st->skipNumberOfBytes;
+  a.abs_base = file ? file->base : 0;
   a.fs = st->samplingFreq;
   a.codeFreqBasis = st->codeFreqBasis;
   a.codeLength = (double)st->codeLength;
@@ -1087,8 +1104,32 @@ extern "C" int sgx_track(const int8_t* rec, int64_t rec_stride, const int64_t* r
     SGX_CUDA(cudaEventRecord(g_trk.ev[1], s));                     // the copy stream starts after earlier work on s
     SGX_CUDA(cudaStreamWaitEvent(g_trk.copy_stream, g_trk.ev[1], 0));
     int c = 0;
+    if (file) chunk = file->chunk;
     for (long long off = 0; off < max_len; off += chunk, ++c) {
       const long long width = (max_len - off) < chunk ? (max_len - off) : chunk;
+      if (file) {
+        // pread into the pinned buffer that is free (its previous copy has completed), convert if needed, copy
+        int8_t* hb = g_trk.pin[c & 1];
+        if (c >= 2) SGX_CUDA(cudaEventSynchronize(g_trk.pin_ev[c & 1]));
+        const size_t bytes = (size_t)width * file->sample_bytes;
+        size_t got = 0;
+        while (got < bytes) {
+          const ssize_t r = pread(file->fd, (char*)hb + got, bytes - got, (off_t)((file->base + off) * file->sample_bytes + (long long)got));
+          if (r <= 0) return fail(SGX_ERR_ARG, "sgx_track_file", "short read from the recording file");
+          got += (size_t)r;
+        }
+        if (file->sample_bytes == 2) {   // in place, front to back: sample i lands in byte i
+          const int16_t* src = (const int16_t*)hb;
+          for (long long i = 0; i < width; ++i) {
+            const int v = src[i];
+            if (v < -128 || v > 127) file->bad_value = 1;
+            hb[i] = (int8_t)v;
+          }
+          if (file->bad_value) return fail(SGX_ERR_ARG, "sgx_track_file", "int16 sample outside the int8 range of the correlators");
+        }
+        SGX_CUDA(cudaMemcpyAsync(g_trk.rec.as<int8_t>() + off, hb, (size_t)width, cudaMemcpyHostToDevice, g_trk.copy_stream));
+        SGX_CUDA(cudaEventRecord(g_trk.pin_ev[c & 1], g_trk.copy_stream));
+      } else
       SGX_CUDA(cudaMemcpy2DAsync(g_trk.rec.as<int8_t>() + off, (size_t)stride, rec + off, (size_t)rec_stride, (size_t)width,
                                  (size_t)n_recordings, cudaMemcpyHostToDevice, g_trk.copy_stream));
       SGX_CUDA(cudaEventRecord(g_trk.ev[0], g_trk.copy_stream));
@@ -1122,4 +1163,70 @@ extern "C" int sgx_track(const int8_t* rec, int64_t rec_stride, const int64_t* r
   if (rc == SGX_ERR_SHORT) return fail(rc, "sgx_track", "Not able to read the specified number of samples for tracking");
   if (rc != SGX_OK) return fail(rc, "sgx_track", "loop state left the supported range");
   return SGX_OK;
+}
+
+extern "C" int sgx_track(const int8_t* rec, int64_t rec_stride, const int64_t* rec_len,
+                         int32_t n_recordings, const sgx_channel* ch, int32_t n_channels,
+                         const sgx_settings* st, const int8_t* ca_chips, double* out,
+                         int32_t* ms_done, void* cuda_stream) {
+  if (sgx_device_count() <= 0) return fail(SGX_ERR_NODEV, "sgx_track", "no CUDA device");
+  SGX_API_GUARD();
+  return track_core(rec, rec_stride, rec_len, n_recordings, ch, n_channels, st, ca_chips, out, ms_done, cuda_stream,
+                    nullptr);
+}
+
+// File ingest (replaces fid.seek / np.fromfile of tracking.py:107, :154 and the
+// dataType / skipNumberOfBytes handling of initialize.py:102, :466-481): the recording is read with pread() in chunks
+// into two pinned staging buffers and copied to HBM on the copy stream while the kernel tracks the periods that are
+// already resident.  Only the window tracking can touch is read: from the first sample any channel starts at to
+// msToProcess code periods (+ margin) after the last one -- never the whole file, never a pageable copy.
+extern "C" int sgx_track_file(const char* path, int32_t sample_bytes, const sgx_channel* ch, int32_t n_channels,
+                              const sgx_settings* st, const int8_t* ca_chips, double* out, int32_t* ms_done,
+                              int64_t chunk_samples, int64_t* window /* [2]: first sample, samples read; may be NULL */,
+                              void* cuda_stream) {
+  if (sgx_device_count() <= 0) return fail(SGX_ERR_NODEV, "sgx_track_file", "no CUDA device");
+  SGX_API_GUARD();
+  if (!path || !ch || !st || n_channels <= 0 || (sample_bytes != 1 && sample_bytes != 2))
+    return fail(SGX_ERR_ARG, "sgx_track_file", "null pointer, or dataType other than int8 / int16");
+  const int fd = open(path, O_RDONLY);
+  if (fd < 0) return fail(SGX_ERR_ARG, "sgx_track_file", "cannot open the recording file");
+  struct stat sb;
+  if (fstat(fd, &sb) != 0) { close(fd); return fail(SGX_ERR_ARG, "sgx_track_file", "cannot stat the recording file"); }
+  const long long file_samples = (long long)sb.st_size / sample_bytes;
+  double cp_min = 1e300, cp_max = -1e300;
+  for (int i = 0; i < n_channels; ++i)
+    if (ch[i].prn > 0) { cp_min = ch[i].codePhase < cp_min ? ch[i].codePhase : cp_min; cp_max = ch[i].codePhase > cp_max ? ch[i].codePhase : cp_max; }
+  if (cp_max < cp_min) { cp_min = cp_max = 0.0; }
+  const long long skip = st->skipNumberOfBytes / sample_bytes;
+  FileSrc fs;
+  fs.fd = fd;
+  fs.sample_bytes = sample_bytes;
+  fs.bad_value = 0;
+  fs.base = (skip + (long long)cp_min) & ~15LL;
+  // msToProcess code periods per channel; the period length follows the code Doppler (<= 1e-5 relative): 1e-4 + 2 periods
+  const double need = (double)(skip + (long long)cp_max - fs.base) + ((double)st->msToProcess * (1.0 + 1e-4) + 2.0) * st->samplesPerCode + 64.0;
+  fs.len = file_samples - fs.base;
+  if (fs.len > (long long)need) fs.len = (long long)need;
+  if (fs.len <= 0) { close(fd); return fail(SGX_ERR_SHORT, "sgx_track_file", "Not able to read the specified number of samples for tracking"); }
+  fs.chunk = chunk_samples > 0 ? chunk_samples : 1024LL * st->samplesPerCode;
+  fs.chunk = (fs.chunk + 15) & ~15LL;
+  const size_t pin_bytes = (size_t)fs.chunk * sample_bytes;
+  if (g_trk.pin_cap < pin_bytes) {
+    for (int i = 0; i < 2; ++i) {
+      if (g_trk.pin[i]) cudaFreeHost(g_trk.pin[i]);
+      g_trk.pin[i] = nullptr;
+      if (cudaHostAlloc((void**)&g_trk.pin[i], pin_bytes, cudaHostAllocDefault) != cudaSuccess) {
+        g_trk.pin_cap = 0;
+        close(fd);
+        return fail(SGX_ERR_CUDA, "cudaHostAlloc", "pinned staging buffers");
+      }
+      if (!g_trk.pin_ev[i]) cudaEventCreateWithFlags(&g_trk.pin_ev[i], cudaEventDisableTiming);
+    }
+    g_trk.pin_cap = pin_bytes;
+  }
+  if (window) { window[0] = fs.base; window[1] = fs.len; }
+  const int64_t rec_len = fs.len;
+  const int rc = track_core(nullptr, 0, &rec_len, 1, ch, n_channels, st, ca_chips, out, ms_done, cuda_stream, &fs);
+  close(fd);
+  return rc;
 }

@@ -18,6 +18,7 @@ from . import _native
 from .settings import to_pod
 
 FIELDS = _native.TRACK_FIELDS
+FILE_CHUNK_SAMPLES = 0          # samples per staging buffer of the file ingest (0: the library's default, 1024 code periods)
 RESULT_DTYPE = [('status', 'S1')] + [(f, 'object') for f in FIELDS] + [('PRN', 'int64')]
 
 
@@ -52,21 +53,44 @@ class Result(object):
         pass
 
 
-def _load_recording(fid):
-    """The bytes the reference would reach through fid.seek/np.fromfile, as one int8 array
-    (or a CUDA tensor passed through)."""
+SAMPLE_BYTES = {"int8": 1, "b": 1, "schar": 1, "int16": 2, "short": 2}
+
+
+def _sample_bytes(settings):
+    """``settings.dataType`` (initialize.py:102) -> bytes per sample; anything but int8 / int16 is rejected."""
+    dt = str(getattr(settings, "dataType", "int8"))
+    if dt not in SAMPLE_BYTES:
+        raise _native.NativeError(-2, "dataType %r is not supported (int8, int16)" % dt)
+    return SAMPLE_BYTES[dt]
+
+
+def _file_path(fid):
+    """Path of a recording given as a path or as an open file object (the reference's form), else None."""
+    import os
+    if isinstance(fid, (str, bytes, os.PathLike)):
+        return os.fspath(fid)
+    name = getattr(fid, "name", None)
+    if isinstance(name, (str, bytes)) and os.path.exists(name):
+        return name
+    return None
+
+
+def _load_recording(fid, settings=None):
+    """In-memory forms of a recording: an int8 numpy array, a CUDA tensor (passed through), or a file-like object
+    without a path (read once).  Files with a path never come here: they are streamed (``sgx_track_file``)."""
     if hasattr(fid, "data_ptr"):            # torch tensor
         return fid
     if isinstance(fid, np.ndarray):
         assert fid.dtype == np.int8 and fid.ndim == 1
         return np.ascontiguousarray(fid)
-    if isinstance(fid, str):
-        return np.fromfile(fid, dtype=np.int8)
-    name = getattr(fid, "name", None)
-    if isinstance(name, str):
-        return np.fromfile(name, dtype=np.int8)
     fid.seek(0)
-    return np.frombuffer(fid.read(), dtype=np.int8)
+    raw = fid.read()
+    if settings is not None and _sample_bytes(settings) == 2:
+        x = np.frombuffer(raw, dtype="<i2")
+        if x.size and (x.min() < -128 or x.max() > 127):
+            raise _native.NativeError(-2, "int16 sample outside the int8 range of the correlators")
+        return x.astype(np.int8)
+    return np.frombuffer(raw, dtype=np.int8)
 
 
 def track_batch(recordings, rec_len, channel_sets, settings, out=None, stream=0):
@@ -91,10 +115,24 @@ def track_batch(recordings, rec_len, channel_sets, settings, out=None, stream=0)
 
 def tracking(fid, channel, settings):
     """``[trackResults, channel] = tracking(fid, channel, settings)`` (reference tracking.py:13-295)."""
-    data = _load_recording(fid)
-    n = int(data.numel() if hasattr(data, "data_ptr") else data.size)
-    rec = data.reshape(1, n) if not hasattr(data, "data_ptr") else data.view(1, n)
-    rc, out, done = track_batch(rec, [n], [channel], settings)
+    path = _file_path(fid)
+    if path is not None:
+        # on-disk recording: pread -> two pinned staging buffers -> HBM, overlapped with tracking; only the window the
+        # channels can touch is read (tracking.py:107, :154; initialize.py:102, :466-481)
+        L = _native.lib()
+        pod = to_pod(settings)
+        c = int(settings.numberOfChannels)
+        chans = _native.make_channels([int(channel.PRN[i]) for i in range(c)],
+                                      [float(channel.acquiredFreq[i]) for i in range(c)],
+                                      [float(channel.codePhase[i]) for i in range(c)])
+        out = np.zeros((1, c, len(FIELDS), pod.msToProcess), dtype=np.float64)
+        rc, done, _ = L.track_file(path, _sample_bytes(settings), chans, pod, _native.ca_chips_int8(), out,
+                                   chunk_samples=FILE_CHUNK_SAMPLES)
+    else:
+        data = _load_recording(fid, settings)
+        n = int(data.numel() if hasattr(data, "data_ptr") else data.size)
+        rec = data.reshape(1, n) if not hasattr(data, "data_ptr") else data.view(1, n)
+        rc, out, done = track_batch(rec, [n], [channel], settings)
     if rc == _native.SGX_ERR_SHORT:
         print('Not able to read the specified number of samples for tracking, exiting!')
         if hasattr(fid, "close"):

@@ -369,6 +369,8 @@ static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = aligned_alloc(25
 template <class T> static inline cudaError_t cudaMalloc(T** p, size_t n) { return cudaMalloc((void**)p, n); }
 static inline cudaError_t cudaFree(void* p) { free(p); return 0; }
 static inline cudaError_t cudaMallocHost(void** p, size_t n) { return cudaMalloc(p, n); }
+enum { cudaHostAllocDefault = 0 };
+static inline cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { return cudaMalloc(p, n); }
 static inline cudaError_t cudaFreeHost(void* p) { free(p); return 0; }
 static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return 0; }
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = 0) { memcpy(d, s, n); return 0; }
