@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "sgx_fft.cuh"
+#include "sgx_fine.cuh"  // pruned 2048 x 2048 fine-frequency transform for nfft = 2^22 (own translation unit)
 #include "sgx_pfa.cuh"   // prime-factor search kernel for N = 31*7*16*11 (own translation unit)
 
 namespace sgx {
@@ -117,10 +118,6 @@ struct SrcMulSel {  // async variant of ProMulSel
     src = spec + (((long long)rec * d.blocks + s.blk) * d.nbins + s.bin) * n;
     aux = codeF + (long long)(d.prn_first + prn) * n;
   }
-};
-
-struct FineItem {
-  int rec, prn, codePhase, pad;
 };
 
 // A10: (x - mean) * code, zero padded.  The reference's transform has nfft = 8 * 2^ceil(log2(nvalid)) points of which
@@ -757,6 +754,16 @@ extern "C" int sgx_acquire(const int8_t* sig, int64_t rec_stride, int64_t n_samp
         a.findex.reserve(sizeof(int) * nf) || a.work0.reserve(wfine) || a.work1.reserve(wfine))
       return fail(SGX_ERR_CUDA, "cudaMalloc", "fine search scratch");
     SGX_CUDA(cudaMemcpyAsync(a.fitems.p, items, sizeof(FineItem) * nf, cudaMemcpyHostToDevice, s));
+    static const bool fine2 = !(getenv("SGX_ACQ_FINE2") && getenv("SGX_ACQ_FINE2")[0] == '0');
+    if (fine2 && a.nfft == fine::NFFT) {
+      fine::Args fa;
+      fa.sig = d_sig; fa.rec_stride = stride; fa.sums = (const long long*)a.sums.p; fa.n_samples = (long long)n_samples;
+      fa.chips = a.chips.as<int8_t>(); fa.idx = a.fidx.as<unsigned short>(); fa.items = a.fitems.as<FineItem>();
+      fa.nvalid = a.nvalid; fa.lo = 4; fa.hi = uniq - 5;
+      fa.w2048 = nullptr; fa.wlo = nullptr; fa.y = nullptr; fa.partial = nullptr; fa.stripped = nullptr; fa.strip_stride = 0;
+      rc = fine::run(fa, nf, a.findex.as<int>(), s);
+      if (rc) return rc;
+    } else {
     for (int f0 = 0; f0 < nf; f0 += fchunk) {
       const int cnt = nf - f0 < fchunk ? nf - f0 : fchunk;
       EpiFine ef;
@@ -776,6 +783,7 @@ extern "C" int sgx_acquire(const int8_t* sig, int64_t rec_stride, int64_t n_samp
     }
     SGX_COUNTED_LAUNCH(fine_reduce_kernel, dim3(nf), dim3(fft::FFT_THREADS), 0, s, a.fpartial.as<unsigned long long>(),
                        nt_f * FINE_SUBS, nf, a.findex.as<int>());
+    }
     SGX_CUDA(cudaGetLastError());
     std::vector<int> h_idx_v(nf);
     int* h_idx = h_idx_v.data();

@@ -13,6 +13,10 @@ struct PeakSel {  // per (rec, prn): result of A8/A9 first half
   float peak;
 };
 
+struct FineItem {   // a detection handed to the fine-frequency search
+  int rec, prn, codePhase, pad;
+};
+
 // acquisition.py:147-159: is code phase i a candidate for the second peak?
 __device__ __forceinline__ bool second_peak_candidate(int i, int c, int w, int n) {
   const int lo = c - w, hi = c + w;

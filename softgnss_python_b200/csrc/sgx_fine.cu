@@ -1,0 +1,249 @@
+// Fine-frequency search (A10, acquisition.py:170-193) for nfft = 2^22 as a pruned, real-input two-step transform.
+//
+// The reference transforms 10 ms of code-stripped samples, nvalid = 381 920 real values zero-padded to
+// nfft = 8 * 2^19 = 4 194 304 points, and takes the arg-max of |X[k]| over k in [4, nfft/2 - 4).  The first version
+// (sgx_acq.cu, ProFine/EpiFine) evaluates five 2^19-point sub-transforms in three HBM passes each: 80 MB of traffic
+// and 26 launches of small tiles per 25 detections (profiles/ncu_summary_r2_v2.md: the 64-point middle pass sits at
+// its barriers, 38 % issue utilisation).  Here the 2^22-point transform is split 2048 x 2048:
+//
+//   n = n1 + 2048 n2,  k = k2 + 2048 k1:
+//   X[k2 + 2048 k1] = sum_n1  w_N^(n1 k2) * [ sum_n2 x[n1 + 2048 n2] w_2048^(n2 k2) ]  *  w_2048^(n1 k1)
+//
+//   step 1 (fine_cols_kernel): 2048-point transforms over n2 for every column n1.  Only the first 187 rows are
+//     non-zero (zero padding), and the input is real: two real columns travel as one complex column and are separated
+//     afterwards, and only k2 = 0..1024 is kept (the other half is the mirror image).  The inter-step twiddle
+//     w_N^(n1 k2) is applied on the way out.  Output Y[k2][n1], 16.8 MB per detection.
+//   step 2 (fine_rows_kernel): 2048-point transforms over n1 for the 1025 rows k2; outputs k1 < 1024 are the bins
+//     k2 + 2048 k1, outputs k1 >= 1024 the mirrored bins (2048 - k2) + 2048 (2047 - k1) (real input: |X[N-k]| = |X[k]|),
+//     so every bin below nfft/2 appears exactly once.  |.|^2 and the slice-relative arg-max are taken from the
+//     registers of the last butterfly; nothing is written but one key per (detection, tile).
+//
+// Both kernels keep a whole [2048][4] tile in shared memory (80 KB, two CTAs per SM) and run the transform in place (decimation in
+// frequency, radices 16 x 16 x 8, output in digit-reversed positions -- the consumer computes the index instead of
+// permuting).  Traffic per detection: 33.6 MB instead of 80; two launches for all detections of a call.
+#include "sgx_fine.cuh"
+
+namespace sgx {
+namespace fine {
+
+constexpr int R = 2048;        // length of both steps
+constexpr int C = 4;           // complex columns of a tile (80 KB of shared memory: two CTAs per SM)
+constexpr int CP = C;          // row stride; bank conflicts are avoided by the column swizzle below, not by padding
+constexpr int NT = 256;
+constexpr int ROWS_KEPT = R / 2 + 1;   // k2 = 0..1024
+
+// Element (row, column c) of a tile lives at row*4 + (c ^ swz(row)).  With 8-byte elements a half-warp's 16 accesses
+// are conflict-free when they fall into 16 different 8-byte bank pairs: the butterfly stages of block sizes 2048 and
+// 128 touch 4 consecutive rows x 4 columns per half-warp (any swizzle works), the last stage rows 8 apart, and the
+// transposed tile load of step 2 sixteen consecutive rows of one column -- both need the swizzle to differ across rows
+// that are 4, 8, 16 and 24 apart.
+__device__ __forceinline__ int at(int row, int c) { return row * CP + (c ^ (((row >> 2) ^ (row >> 4)) & 3)); }
+
+__host__ __device__ constexpr int digit_rev(int k) {   // k = ka + 16 kb + 256 kc  ->  position ka*128 + kb*8 + kc
+  return (k & 15) * 128 + ((k >> 4) & 15) * 8 + (k >> 8);
+}
+
+// One decimation-in-frequency stage, in place: blocks of L rows, radix r; twiddles w_L^(j u) = W[(R/L) j u mod R].
+template <int r, int L>
+__device__ __forceinline__ void dif_stage(cpx* x, const cpx* __restrict__ W, int tid) {
+  constexpr int q = L / r;
+  for (int idx = tid; idx < (R / r) * C; idx += NT) {
+    const int c = idx % C, t = idx / C;
+    const int j = t % q, row0 = (t / q) * L + j;
+    cpx v[r];
+#pragma unroll
+    for (int u = 0; u < r; ++u) v[u] = x[at(row0 + u * q, c)];
+    fft::Dft<r, false>::run(v);
+    if (L > r) {
+#pragma unroll
+      for (int u = 1; u < r; ++u) v[u] = fft::cmulf(v[u], W[((R / L) * j * u) & (R - 1)]);
+    }
+#pragma unroll
+    for (int u = 0; u < r; ++u) x[at(row0 + u * q, c)] = v[u];
+  }
+}
+
+__device__ __forceinline__ void fft2048_inplace(cpx* x, const cpx* W, int tid) {
+  dif_stage<16, 2048>(x, W, tid);
+  __syncthreads();
+  dif_stage<16, 128>(x, W, tid);
+  __syncthreads();
+  dif_stage<8, 8>(x, W, tid);
+  __syncthreads();
+}
+
+// (x - mean) * code for the nvalid samples of every detection, zero-padded to whole rows of 2048 (acquisition.py:177)
+__global__ void strip_kernel(Args a, int padded) {
+  const FineItem it = a.items[blockIdx.y];
+  const float mean = (float)((double)a.sums[it.rec] / (double)a.n_samples);
+  const int8_t* sig = a.sig + (long long)it.rec * a.rec_stride + it.codePhase;
+  const int8_t* chips = a.chips + it.prn * 1023;
+  float* out = a.stripped + (long long)blockIdx.y * a.strip_stride;
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < padded; n += gridDim.x * blockDim.x)
+    out[n] = n < a.nvalid ? ((float)sig[n] - mean) * (float)chips[a.idx[n]] : 0.f;
+}
+
+// step 1: blockIdx.x = column tile (2 C real columns), blockIdx.y = detection
+__global__ void __launch_bounds__(NT, 2) fine_cols_kernel(Args a) {
+  SGX_DYN_SMEM(smem);
+  cpx* x = reinterpret_cast<cpx*>(smem);
+  cpx* W = x + R * CP;
+  const int tid = threadIdx.x, tile = blockIdx.x;
+  for (int i = tid; i < R; i += NT) W[i] = a.w2048[i];
+  const int n_rows = (a.nvalid + R - 1) / R;    // rows n2 that hold samples
+  // code-stripped samples of this detection (strip_kernel), padded with zeros to whole rows: two reals = one element
+  const cpx* xs = reinterpret_cast<const cpx*>(a.stripped + (long long)blockIdx.y * a.strip_stride) + tile * C;
+  for (int idx = tid; idx < R * C; idx += NT) {
+    const int c = idx % C, n2 = idx / C;
+    x[at(n2, c)] = n2 < n_rows ? __ldg(xs + (long long)n2 * (R / 2) + c) : make_float2(0.f, 0.f);
+  }
+  __syncthreads();
+  fft2048_inplace(x, W, tid);
+  // separate the two real columns of every complex column, apply w_N^(n1 k2), store Y[k2][n1]
+  cpx* out = a.y + ((long long)blockIdx.y * ROWS_KEPT) * R + tile * 2 * C;
+  for (int idx = tid; idx < ROWS_KEPT * C; idx += NT) {
+    const int c = idx % C, k2 = idx / C;
+    const cpx zp = x[at(digit_rev(k2), c)], zm = x[at(digit_rev((R - k2) & (R - 1)), c)];
+    cpx ya = make_float2(zp.x + zm.x, zp.y - zm.y);           // 2 X_a[k2]
+    cpx yb = make_float2(zp.y + zm.y, zm.x - zp.x);           // 2 X_b[k2]
+    const int n1 = tile * 2 * C + 2 * c;
+    const int ma = n1 * k2, mb = ma + k2;                       // < 2^21: no wrap modulo N = 2^22
+    ya = fft::cmulf(ya, fft::cmulf(W[ma >> 11], a.wlo[ma & (R - 1)]));
+    yb = fft::cmulf(yb, fft::cmulf(W[mb >> 11], a.wlo[mb & (R - 1)]));
+    *reinterpret_cast<float4*>(out + (long long)k2 * R + 2 * c) = make_float4(ya.x, ya.y, yb.x, yb.y);
+  }
+}
+
+// step 2: blockIdx.x = row tile (C values of k2), blockIdx.y = detection
+__global__ void __launch_bounds__(NT, 2) fine_rows_kernel(Args a) {
+  SGX_DYN_SMEM(smem);
+  cpx* x = reinterpret_cast<cpx*>(smem);
+  cpx* W = x + R * CP;
+  __shared__ unsigned long long red[NT / 32];
+  const int tid = threadIdx.x, tile = blockIdx.x;
+  for (int i = tid; i < R; i += NT) W[i] = a.w2048[i];
+  const cpx* in = a.y + ((long long)blockIdx.y * ROWS_KEPT + tile * C) * R;
+  const int rows = min(C, ROWS_KEPT - tile * C);
+  for (int rr = 0; rr < C; ++rr) {
+    for (int n1 = tid; n1 < R; n1 += NT)
+      x[at(n1, rr)] = rr < rows ? __ldcs(in + (long long)rr * R + n1) : make_float2(0.f, 0.f);
+  }
+  __syncthreads();
+  dif_stage<16, 2048>(x, W, tid);
+  __syncthreads();
+  dif_stage<16, 128>(x, W, tid);
+  __syncthreads();
+  // last stage (radix 8, no twiddles): outputs stay in registers -> |.|^2, bin index, arg-max
+  unsigned long long best = 0ull;
+  for (int idx = tid; idx < (R / 8) * C; idx += NT) {
+    const int c = idx % C, t = idx / C;      // t = ka*16 + kb: the outputs of this butterfly are k1 = ka + 16 kb + 256 u
+    cpx v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = x[at(t * 8 + u, c)];
+    fft::Dft<8, false>::run(v);
+    if (c < rows) {
+      const int k2 = tile * C + c;
+      const int k1lo = (t >> 4) + 16 * (t & 15);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int k1 = k1lo + 256 * u;
+        int k;
+        if (k1 < R / 2) k = k2 + R * k1;
+        else if (k2 > 0 && k2 < R / 2) k = (R - k2) + R * (R - 1 - k1);
+        else continue;
+        if (k < a.lo || k >= a.hi) continue;
+        const unsigned long long key = fft::peak_key(fmaf(v[u].x, v[u].x, v[u].y * v[u].y), (unsigned)(k - a.lo));
+        best = key > best ? key : best;
+      }
+    }
+  }
+#pragma unroll
+  for (int msk = 16; msk > 0; msk >>= 1) {
+    const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, msk);
+    best = o > best ? o : best;
+  }
+  if ((tid & 31) == 0) red[tid >> 5] = best;
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < NT / 32; ++w) best = red[w] > best ? red[w] : best;
+    a.partial[(long long)blockIdx.y * gridDim.x + tile] = best;
+  }
+}
+
+__global__ void fine_argmax_kernel(const unsigned long long* partial, int ntiles, int* index) {
+  __shared__ unsigned long long red[4];
+  unsigned long long best = 0ull;
+  for (int t = threadIdx.x; t < ntiles; t += blockDim.x) {
+    const unsigned long long k = partial[(long long)blockIdx.x * ntiles + t];
+    best = k > best ? k : best;
+  }
+#pragma unroll
+  for (int msk = 16; msk > 0; msk >>= 1) {
+    const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, msk);
+    best = o > best ? o : best;
+  }
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)blockDim.x / 32; ++w) best = red[w] > best ? red[w] : best;
+    index[blockIdx.x] = (int)fft::key_index(best);
+  }
+}
+
+__global__ void fine_tables_kernel(cpx* w2048, cpx* wlo) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R) return;
+  double s, c;
+  sincospi(-2.0 * (double)i / (double)R, &s, &c);
+  w2048[i] = make_float2((float)c, (float)s);
+  sincospi(-2.0 * (double)i / (double)NFFT, &s, &c);
+  wlo[i] = make_float2((float)c, (float)s);
+}
+
+struct Scratch {
+  DevBuf w2048, wlo, y, partial, stripped;
+  bool tables = false;
+};
+static Scratch g_fine;
+
+int run(Args a, int n_items, int* d_index, cudaStream_t s) {
+  if (n_items <= 0) return SGX_OK;
+  Scratch& g = g_fine;
+  if (!g.tables) {
+    if (g.w2048.reserve(sizeof(cpx) * R) || g.wlo.reserve(sizeof(cpx) * R)) return fail(SGX_ERR_CUDA, "cudaMalloc", "fine tables");
+    SGX_COUNTED_LAUNCH(fine_tables_kernel, dim3(R / 256), dim3(256), 0, s, g.w2048.as<cpx>(), g.wlo.as<cpx>());
+    g.tables = true;
+  }
+  const int col_tiles = R / (2 * C), row_tiles = (ROWS_KEPT + C - 1) / C;
+  long long chunk = (2LL << 30) / ((long long)sizeof(cpx) * ROWS_KEPT * R);      // detections per 2 GB of Y
+  if (chunk < 1) chunk = 1;
+  if (chunk > n_items) chunk = n_items;
+  const int padded = (a.nvalid + R - 1) / R * R;
+  if (g.stripped.reserve(sizeof(float) * (size_t)chunk * padded)) return fail(SGX_ERR_CUDA, "cudaMalloc", "fine search scratch");
+  a.stripped = g.stripped.as<float>();
+  a.strip_stride = padded;
+  if (g.y.reserve(sizeof(cpx) * (size_t)chunk * ROWS_KEPT * R) ||
+      g.partial.reserve(sizeof(unsigned long long) * (size_t)chunk * row_tiles))
+    return fail(SGX_ERR_CUDA, "cudaMalloc", "fine search scratch");
+  const size_t smem = sizeof(cpx) * ((size_t)R * CP + R);
+  SGX_CUDA(cudaFuncSetAttribute(fine_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SGX_CUDA(cudaFuncSetAttribute(fine_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  a.w2048 = g.w2048.as<cpx>();
+  a.wlo = g.wlo.as<cpx>();
+  a.y = g.y.as<cpx>();
+  a.partial = g.partial.as<unsigned long long>();
+  const FineItem* items = a.items;
+  for (int i0 = 0; i0 < n_items; i0 += (int)chunk) {
+    const int cnt = n_items - i0 < chunk ? n_items - i0 : (int)chunk;
+    a.items = items + i0;
+    SGX_COUNTED_LAUNCH(strip_kernel, dim3(64, cnt), dim3(256), 0, s, a, padded);
+    SGX_COUNTED_LAUNCH(fine_cols_kernel, dim3(col_tiles, cnt), dim3(NT), smem, s, a);
+    SGX_COUNTED_LAUNCH(fine_rows_kernel, dim3(row_tiles, cnt), dim3(NT), smem, s, a);
+    SGX_COUNTED_LAUNCH(fine_argmax_kernel, dim3(cnt), dim3(128), 0, s, a.partial, row_tiles, d_index + i0);
+  }
+  SGX_CUDA(cudaGetLastError());
+  return SGX_OK;
+}
+
+}  // namespace fine
+}  // namespace sgx

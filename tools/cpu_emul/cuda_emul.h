@@ -325,6 +325,7 @@ static inline unsigned long long __umul64hi(unsigned long long a, unsigned long 
 }
 template <class T> static inline T __ldg(const T* p) { return *p; }
 template <class T> static inline T __ldcg(const T* p) { return *p; }
+template <class T> static inline T __ldcs(const T* p) { return *p; }
 template <class T> static inline void __stcg(T* p, T v) { *p = v; }
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 static inline float __fdividef(float a, float b) { return a / b; }
