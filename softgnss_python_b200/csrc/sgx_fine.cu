@@ -18,7 +18,7 @@
 //     so every bin below nfft/2 appears exactly once.  |.|^2 and the slice-relative arg-max are taken from the
 //     registers of the last butterfly; nothing is written but one key per (detection, tile).
 //
-// Both kernels keep a whole [2048][4] tile in shared memory (80 KB, two CTAs per SM) and run the transform in place (decimation in
+// Both kernels keep a whole [2048][4] tile in shared memory (64 KB; step 1 adds its twiddle table: two CTAs per SM, step 2 three) and run the transform in place (decimation in
 // frequency, radices 16 x 16 x 8, output in digit-reversed positions -- the consumer computes the index instead of
 // permuting).  Traffic per detection: 33.6 MB instead of 80; two launches for all detections of a call.
 #include "sgx_fine.cuh"
@@ -27,7 +27,7 @@ namespace sgx {
 namespace fine {
 
 constexpr int R = 2048;        // length of both steps
-constexpr int C = 4;           // complex columns of a tile (80 KB of shared memory: two CTAs per SM)
+constexpr int C = 4;           // complex columns of a tile (64 KB of shared memory per tile)
 constexpr int CP = C;          // row stride; bank conflicts are avoided by the column swizzle below, not by padding
 constexpr int NT = 256;
 constexpr int ROWS_KEPT = R / 2 + 1;   // k2 = 0..1024
@@ -44,7 +44,8 @@ __host__ __device__ constexpr int digit_rev(int k) {   // k = ka + 16 kb + 256 k
 }
 
 // One decimation-in-frequency stage, in place: blocks of L rows, radix r; twiddles w_L^(j u) = W[(R/L) j u mod R].
-template <int r, int L>
+// WG: the twiddle table is read from global memory through L1 (step 2: three CTAs per SM), else from shared memory.
+template <int r, int L, bool WG>
 __device__ __forceinline__ void dif_stage(cpx* x, const cpx* __restrict__ W, int tid) {
   constexpr int q = L / r;
   for (int idx = tid; idx < (R / r) * C; idx += NT) {
@@ -56,7 +57,10 @@ __device__ __forceinline__ void dif_stage(cpx* x, const cpx* __restrict__ W, int
     fft::Dft<r, false>::run(v);
     if (L > r) {
 #pragma unroll
-      for (int u = 1; u < r; ++u) v[u] = fft::cmulf(v[u], W[((R / L) * j * u) & (R - 1)]);
+      for (int u = 1; u < r; ++u) {
+        const int wi = ((R / L) * j * u) & (R - 1);
+        v[u] = fft::cmulf(v[u], WG ? __ldg(W + wi) : W[wi]);
+      }
     }
 #pragma unroll
     for (int u = 0; u < r; ++u) x[at(row0 + u * q, c)] = v[u];
@@ -64,11 +68,11 @@ __device__ __forceinline__ void dif_stage(cpx* x, const cpx* __restrict__ W, int
 }
 
 __device__ __forceinline__ void fft2048_inplace(cpx* x, const cpx* W, int tid) {
-  dif_stage<16, 2048>(x, W, tid);
+  dif_stage<16, 2048, false>(x, W, tid);
   __syncthreads();
-  dif_stage<16, 128>(x, W, tid);
+  dif_stage<16, 128, false>(x, W, tid);
   __syncthreads();
-  dif_stage<8, 8>(x, W, tid);
+  dif_stage<8, 8, false>(x, W, tid);
   __syncthreads();
 }
 
@@ -108,30 +112,33 @@ __global__ void __launch_bounds__(NT, 2) fine_cols_kernel(Args a) {
     cpx yb = make_float2(zp.y + zm.y, zm.x - zp.x);           // 2 X_b[k2]
     const int n1 = tile * 2 * C + 2 * c;
     const int ma = n1 * k2, mb = ma + k2;                       // < 2^21: no wrap modulo N = 2^22
-    ya = fft::cmulf(ya, fft::cmulf(W[ma >> 11], a.wlo[ma & (R - 1)]));
-    yb = fft::cmulf(yb, fft::cmulf(W[mb >> 11], a.wlo[mb & (R - 1)]));
+    ya = fft::cmulf(ya, fft::cmulf(W[ma >> 11], __ldg(a.wlo + (ma & (R - 1)))));
+    yb = fft::cmulf(yb, fft::cmulf(W[mb >> 11], __ldg(a.wlo + (mb & (R - 1)))));
     *reinterpret_cast<float4*>(out + (long long)k2 * R + 2 * c) = make_float4(ya.x, ya.y, yb.x, yb.y);
   }
 }
 
 // step 2: blockIdx.x = row tile (C values of k2), blockIdx.y = detection
-__global__ void __launch_bounds__(NT, 2) fine_rows_kernel(Args a) {
+__global__ void __launch_bounds__(NT, 3) fine_rows_kernel(Args a) {
   SGX_DYN_SMEM(smem);
   cpx* x = reinterpret_cast<cpx*>(smem);
-  cpx* W = x + R * CP;
+  const cpx* W = a.w2048;
   __shared__ unsigned long long red[NT / 32];
   const int tid = threadIdx.x, tile = blockIdx.x;
-  for (int i = tid; i < R; i += NT) W[i] = a.w2048[i];
   const cpx* in = a.y + ((long long)blockIdx.y * ROWS_KEPT + tile * C) * R;
   const int rows = min(C, ROWS_KEPT - tile * C);
-  for (int rr = 0; rr < C; ++rr) {
-    for (int n1 = tid; n1 < R; n1 += NT)
-      x[at(n1, rr)] = rr < rows ? __ldcs(in + (long long)rr * R + n1) : make_float2(0.f, 0.f);
+#pragma unroll 2
+  for (int n1 = tid; n1 < R; n1 += NT) {     // all rows of a column in flight before the first store
+    cpx v[C];
+#pragma unroll
+    for (int rr = 0; rr < C; ++rr) v[rr] = rr < rows ? __ldcs(in + (long long)rr * R + n1) : make_float2(0.f, 0.f);
+#pragma unroll
+    for (int rr = 0; rr < C; ++rr) x[at(n1, rr)] = v[rr];
   }
   __syncthreads();
-  dif_stage<16, 2048>(x, W, tid);
+  dif_stage<16, 2048, true>(x, W, tid);
   __syncthreads();
-  dif_stage<16, 128>(x, W, tid);
+  dif_stage<16, 128, true>(x, W, tid);
   __syncthreads();
   // last stage (radix 8, no twiddles): outputs stay in registers -> |.|^2, bin index, arg-max
   unsigned long long best = 0ull;
@@ -225,8 +232,9 @@ int run(Args a, int n_items, int* d_index, cudaStream_t s) {
   if (g.y.reserve(sizeof(cpx) * (size_t)chunk * ROWS_KEPT * R) ||
       g.partial.reserve(sizeof(unsigned long long) * (size_t)chunk * row_tiles))
     return fail(SGX_ERR_CUDA, "cudaMalloc", "fine search scratch");
-  const size_t smem = sizeof(cpx) * ((size_t)R * CP + R);
-  SGX_CUDA(cudaFuncSetAttribute(fine_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = sizeof(cpx) * (size_t)R * CP;            // step 2: tile only (twiddles through L1)
+  const size_t smem_cols = smem + sizeof(cpx) * R;              // step 1: tile + twiddle table
+  SGX_CUDA(cudaFuncSetAttribute(fine_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
   SGX_CUDA(cudaFuncSetAttribute(fine_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   a.w2048 = g.w2048.as<cpx>();
   a.wlo = g.wlo.as<cpx>();
@@ -237,7 +245,7 @@ int run(Args a, int n_items, int* d_index, cudaStream_t s) {
     const int cnt = n_items - i0 < chunk ? n_items - i0 : (int)chunk;
     a.items = items + i0;
     SGX_COUNTED_LAUNCH(strip_kernel, dim3(64, cnt), dim3(256), 0, s, a, padded);
-    SGX_COUNTED_LAUNCH(fine_cols_kernel, dim3(col_tiles, cnt), dim3(NT), smem, s, a);
+    SGX_COUNTED_LAUNCH(fine_cols_kernel, dim3(col_tiles, cnt), dim3(NT), smem_cols, s, a);
     SGX_COUNTED_LAUNCH(fine_rows_kernel, dim3(row_tiles, cnt), dim3(NT), smem, s, a);
     SGX_COUNTED_LAUNCH(fine_argmax_kernel, dim3(cnt), dim3(128), 0, s, a.partial, row_tiles, d_index + i0);
   }

@@ -45,6 +45,21 @@ struct R31 {
     hi = make_float2(cr - si, ci + sr);
     lo = make_float2(cr + si, ci - sr);
   }
+  // output pair m = 0..14 from the unrotated arrays (fully unrolled variant: no register moves, 3x the code)
+  template <int m>
+  __device__ __forceinline__ void pair_at(cpx& hi, cpx& lo) const {
+    float cr = x0.x, ci = x0.y, sr = 0.f, si = 0.f;
+#pragma unroll
+    for (int n = 0; n < 15; ++n) {
+      const float c = C31R[(n + m) % 15], s = S31R[n + m];
+      cr = fmaf(A[n].x, c, cr);
+      ci = fmaf(A[n].y, c, ci);
+      sr = fmaf(B[n].x, s, sr);
+      si = fmaf(B[n].y, s, si);
+    }
+    hi = make_float2(cr - si, ci + sr);
+    lo = make_float2(cr + si, ci - sr);
+  }
   __device__ __forceinline__ void rotate() {   // A_n <- A_(n-5 mod 15);  B_n <- B_(n-5), antiperiodic
     cpx tA[15], tB[15];
 #pragma unroll
@@ -162,7 +177,7 @@ __device__ __forceinline__ unsigned long long block_max(unsigned long long key, 
 // Per warp two shared-memory buffers of NA x 4 values: X (work tile) and Y (code-spectrum slice, filled by cp.async
 // one slice ahead); the spectrum slice of the next slice travels in registers while the current one goes through
 // its second stage and the scratch store.  Pass B uses X and Y together as one NB x 8 tile.
-template <int P1, int P2, int P3, int P4, int WARPS, int MINB, bool MASKED>
+template <int P1, int P2, int P3, int P4, int WARPS, int MINB, bool MASKED, bool UNROLL31 = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB) pfa_search_kernel(SearchArgs a) {
   typedef Shape<P1, P2, P3, P4> S;
   static_assert(P1 == 31, "stage 1 is the grouped radix-31 butterfly");
@@ -204,9 +219,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pfa_search_kernel(SearchArgs
   cpx v[P1];
   // code slice `sa` -> Y (two 16-byte copies per row), spectrum slice -> registers
   auto fetch = [&](int sa) {
-    const cpx* q = cod + sa * CA;
-#pragma unroll 1
-    for (int i = lane; i < 2 * NA; i += 32) cp_async16(Y + (i >> 1) * CA + (i & 1) * 2, q + (size_t)(i >> 1) * NB + (i & 1) * 2);
+    // row (lane >> 1) + 16 it, half (lane & 1): constant offsets per iteration, one predicate for the ragged tail
+    const cpx* q = cod + sa * CA + (size_t)(lane >> 1) * NB + (lane & 1) * 2;
+    cpx* yd = Y + (lane >> 1) * CA + (lane & 1) * 2;
+#pragma unroll
+    for (int it = 0; it < (2 * NA + 31) / 32; ++it)
+      if (it < (2 * NA) / 32 || lane + 32 * it < 2 * NA) cp_async16(yd + it * 16 * CA, q + (size_t)it * 16 * NB);
     cp_async_commit();
     if (act) {
       const cpx* p = src + off0 + sa * CA;
@@ -229,6 +247,19 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pfa_search_kernel(SearchArgs
         R31 bf;
         cpx* x = X + ka * CA + ja;
         x[0] = bf.prepare(v, Y + ka * CA + ja, P2 * CA);
+        if (UNROLL31) {
+          cpx hi, lo;
+#define SGX_R31_AT(m)                                          \
+  {                                                            \
+    bf.pair_at<m>(hi, lo);                                     \
+    x[KHI31C[m] * (P2 * CA)] = hi;                             \
+    x[(P1 - KHI31C[m]) * (P2 * CA)] = lo;                      \
+  }
+          constexpr int KHI31C[15] = SGX_R31_KHI;
+          SGX_R31_AT(0) SGX_R31_AT(1) SGX_R31_AT(2) SGX_R31_AT(3) SGX_R31_AT(4) SGX_R31_AT(5) SGX_R31_AT(6) SGX_R31_AT(7)
+          SGX_R31_AT(8) SGX_R31_AT(9) SGX_R31_AT(10) SGX_R31_AT(11) SGX_R31_AT(12) SGX_R31_AT(13) SGX_R31_AT(14)
+#undef SGX_R31_AT
+        } else {
 #pragma unroll 1
         for (int q = 0; q < 3; ++q) {
           cpx hi, lo;
@@ -244,6 +275,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pfa_search_kernel(SearchArgs
           if (q < 2) bf.rotate();
         }
       }
+        }
       __syncwarp();
       // the next slice's operands travel while this slice goes through stage 2 and the scratch store
       if (sa + WARPS < S::NSA) fetch(sa + WARPS);
@@ -300,14 +332,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pfa_search_kernel(SearchArgs
   }
 }
 
-template <int WARPS, int MINB, bool MASKED>
+template <int WARPS, int MINB, bool MASKED, bool UNROLL31 = false>
 static int launch_cfg(SearchArgs args, DevBuf& scratch, cudaStream_t s) {
   typedef SearchShape S;
   int dev = 0, n_sm = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   if (n_sm <= 0) n_sm = 148;
-  auto kfn = pfa_search_kernel<31, 7, 16, 11, WARPS, MINB, MASKED>;
+  auto kfn = pfa_search_kernel<31, 7, 16, 11, WARPS, MINB, MASKED, UNROLL31>;
   const size_t smem = S::smem_per_warp * WARPS;
   SGX_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
@@ -368,14 +400,14 @@ static int launch_search_t(SearchArgs args, DevBuf& scratch, cudaStream_t s) {
   int cfg = 43;   // warps per CTA x CTAs per SM (measured on B200: 4x3 13.9 ms, 6x2 14.6, 12x1 14.5 per 59 392 transforms)
   if (const char* e = getenv("SGX_PFA_CFG")) cfg = atoi(e);
   switch (cfg) {
-    case 43: return launch_cfg<4, 3, MASKED>(args, scratch, s);
     case 72: return launch_cfg<7, 2, MASKED>(args, scratch, s);
     case 82: return launch_cfg<8, 2, MASKED>(args, scratch, s);
     case 121: return launch_cfg<12, 1, MASKED>(args, scratch, s);
     case 141: return launch_cfg<14, 1, MASKED>(args, scratch, s);
     case 161: return launch_cfg<16, 1, MASKED>(args, scratch, s);
     case 62: return launch_cfg<6, 2, MASKED>(args, scratch, s);
-    default: return launch_cfg<4, 3, MASKED>(args, scratch, s);
+    case 43: return launch_cfg<4, 3, MASKED>(args, scratch, s);           // rolled radix-31 groups (21.4 ms per batch)
+    default: return launch_cfg<4, 3, MASKED, true>(args, scratch, s);     // radix-31 butterfly fully unrolled (21.2 ms)
   }
 }
 
