@@ -397,7 +397,7 @@ static int launch_cfg(SearchArgs args, DevBuf& scratch, cudaStream_t s) {
 
 template <bool MASKED>
 static int launch_search_t(SearchArgs args, DevBuf& scratch, cudaStream_t s) {
-  int cfg = 43;   // warps per CTA x CTAs per SM (measured on B200: 4x3 13.9 ms, 6x2 14.6, 12x1 14.5 per 59 392 transforms)
+  int cfg = 143;  // [1]WC: warps per CTA x CTAs per SM (measured on B200, 59 392 transforms: 4x3 13.7 ms, 6x2 14.6, 12x1 14.5; 143 = 4x3 with the radix-31 butterfly unrolled, 13.5 ms)
   if (const char* e = getenv("SGX_PFA_CFG")) cfg = atoi(e);
   switch (cfg) {
     case 72: return launch_cfg<7, 2, MASKED>(args, scratch, s);
