@@ -115,6 +115,9 @@ def transform(name, src):
 
 def build(out_dir=OUT, verbose=False):
     if not os.path.isdir(REF):
+        # away from the build container (GPU box): a scratch copy generated earlier may have travelled with the snapshot
+        if all(os.path.exists(os.path.join(out_dir, m)) for m in MODULES):
+            return out_dir
         raise FileNotFoundError("reference tree %s not present (expected on the GPU box)" % REF)
     os.makedirs(os.path.join(out_dir, "geoFunctions"), exist_ok=True)
     for rel in MODULES:
