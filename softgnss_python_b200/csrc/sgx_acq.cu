@@ -519,6 +519,11 @@ static unsigned long long fnv(const void* p, size_t n, unsigned long long h = 14
 
 typedef pfa::SearchShape SearchShape;
 
+static bool pfa_forward_enabled() {   // SGX_ACQ_PFA_FWD=0: forward transforms through the Stockham engine + permuting store
+  const char* e = getenv("SGX_ACQ_PFA_FWD");
+  return !(e && e[0] == '0');
+}
+
 static bool pfa_enabled() {
   const char* e = getenv("SGX_ACQ_PFA");
   return !(e && e[0] == '0');
@@ -568,7 +573,9 @@ static int ensure_plan(const sgx_settings* st, const int8_t* ca_table, const int
     SGX_CUDA(cudaStreamSynchronize(s));
   }
   // A5: conj(FFT(code)) / n for all 32 PRNs
-  if (a.pfa)
+  if (a.pfa && pfa_forward_enabled())
+    rc = pfa::launch_forward(ProCode{a.table.as<int8_t>(), n1}, 32, a.codeF.as<cpx>(), 1.0f / (float)a.n, 1, a.scratch, s);
+  else if (a.pfa)
     rc = run_fft(a.fwd, false, 32, ProCode{a.table.as<int8_t>(), n1},
                  pfa::StorePerm{a.codeF.as<cpx>(), (long long)a.n, 1.0f / (float)a.n, 1, a.perm.as<int>(), nullptr},
                  a.work0.as<cpx>(), a.work1.as<cpx>(), s);
@@ -650,7 +657,10 @@ extern "C" int sgx_acquire(const int8_t* sig, int64_t rec_stride, int64_t n_samp
   // ---- A6 + forward half of A7: one spectrum per (rec, block, bin) -----------------------------
   if (nspec > 32768 || npr > 32768)
     return fail(SGX_ERR_ARG, "sgx_acquire", "too many recordings in one call (split the batch)");
-  if (a.pfa)
+  if (a.pfa && pfa_forward_enabled())
+    rc = pfa::launch_forward(ProNco{d_sig, stride, a.cps.as<double>(), nbins, blocks, (int)n, 0.0}, nspec, a.spec.as<cpx>(),
+                             1.f, 0, a.scratch, s);
+  else if (a.pfa)
     rc = run_fft(a.fwd, false, nspec, ProNco{d_sig, stride, a.cps.as<double>(), nbins, blocks, (int)n, 0.0},
                  pfa::StorePerm{a.spec.as<cpx>(), n, 1.f, 0, a.perm.as<int>(), nullptr}, a.work0.as<cpx>(), a.work1.as<cpx>(), s);
   else

@@ -1,76 +1,8 @@
 // Prime-factor search kernel (see sgx_pfa.cuh) -- its own translation unit so that it builds in seconds.
 #include "sgx_pfa.cuh"
-#include "sgx_pfa_tables.h"
 
 namespace sgx {
 namespace pfa {
-
-// ---- radix-31 inverse butterfly in three rolled groups of five output pairs --------------------------------------
-// The fully unrolled conjugate-pair butterfly is ~1100 instructions (17 KB); sixteen unsynchronised warps streaming
-// through it (and the rest of a 62 KB kernel) miss the 32 KB L1.5 instruction cache all the time
-// (profiles/ncu_summary_r2_v1.md: `no_instruction` 1.5 stalled warps per issue).  With the pairs taken in the order of
-// the powers of the primitive root 3, cos(2 pi j_n k_m / 31) = C[(n + m) mod 15]: the 15 x 15 cosine matrix is a
-// circulant (the sine matrix a skew-circulant), so output group q = 0, 1, 2 is the same straight-line code applied to
-// the pair arrays rotated by 5 q places -- 400 instructions executed three times, plus 2 x 60 register moves.
-struct R31 {
-  cpx A[15], B[15];   // a'_n = x[j_n] + x[31 - j_n],  b'_n = sg_n (x[j_n] - x[31 - j_n])
-  cpx x0;
-  // v: spectrum values, y: code-spectrum values (row stride ys); returns the DC output
-  __device__ __forceinline__ cpx prepare(const cpx* v, const cpx* y, int ys) {
-    constexpr int J[15] = SGX_R31_J;
-    constexpr int SG[15] = SGX_R31_SG;
-    x0 = fft::cmulf(v[0], y[0]);
-    cpx dc = x0;
-#pragma unroll
-    for (int n = 0; n < 15; ++n) {
-      const cpx p = fft::cmulf(v[J[n]], y[J[n] * ys]), q = fft::cmulf(v[31 - J[n]], y[(31 - J[n]) * ys]);
-      A[n] = fft::cadd(p, q);
-      B[n] = SG[n] > 0 ? fft::csub(p, q) : fft::csub(q, p);
-      dc = fft::cadd(dc, A[n]);
-    }
-    return dc;
-  }
-  // output pair r of the current group: hi -> row KHI31[5 q + r], lo -> row 31 - KHI31[5 q + r]
-  template <int r>
-  __device__ __forceinline__ void pair(cpx& hi, cpx& lo) const {
-    float cr = x0.x, ci = x0.y, sr = 0.f, si = 0.f;
-#pragma unroll
-    for (int n = 0; n < 15; ++n) {
-      const float c = C31R[(n + r) % 15], s = S31R[n + r];
-      cr = fmaf(A[n].x, c, cr);
-      ci = fmaf(A[n].y, c, ci);
-      sr = fmaf(B[n].x, s, sr);
-      si = fmaf(B[n].y, s, si);
-    }
-    hi = make_float2(cr - si, ci + sr);
-    lo = make_float2(cr + si, ci - sr);
-  }
-  // output pair m = 0..14 from the unrotated arrays (fully unrolled variant: no register moves, 3x the code)
-  template <int m>
-  __device__ __forceinline__ void pair_at(cpx& hi, cpx& lo) const {
-    float cr = x0.x, ci = x0.y, sr = 0.f, si = 0.f;
-#pragma unroll
-    for (int n = 0; n < 15; ++n) {
-      const float c = C31R[(n + m) % 15], s = S31R[n + m];
-      cr = fmaf(A[n].x, c, cr);
-      ci = fmaf(A[n].y, c, ci);
-      sr = fmaf(B[n].x, s, sr);
-      si = fmaf(B[n].y, s, si);
-    }
-    hi = make_float2(cr - si, ci + sr);
-    lo = make_float2(cr + si, ci - sr);
-  }
-  __device__ __forceinline__ void rotate() {   // A_n <- A_(n-5 mod 15);  B_n <- B_(n-5), antiperiodic
-    cpx tA[15], tB[15];
-#pragma unroll
-    for (int n = 0; n < 15; ++n) {
-      tA[n] = A[(n + 10) % 15];
-      tB[n] = n < 5 ? make_float2(-B[n + 10].x, -B[n + 10].y) : B[n - 5];
-    }
-#pragma unroll
-    for (int n = 0; n < 15; ++n) { A[n] = tA[n]; B[n] = tB[n]; }
-  }
-};
 
 // Pass B of one transform for one warp: DFT over (k4, k3) of its slices of 8 tauA columns, read from the scratch.
 // MODE 0: maximum of |.|^2 only (hot path: 3 instructions per point; the code phase of the winning row is found by the

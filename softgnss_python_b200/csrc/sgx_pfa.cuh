@@ -23,6 +23,7 @@
 //   transform; two __syncthreads per transform (pass A -> pass B, and the key reduction).
 #pragma once
 #include "sgx_acq_types.cuh"
+#include "sgx_pfa_tables.h"
 
 namespace sgx {
 namespace pfa {
@@ -73,6 +74,210 @@ struct StorePerm {
   }
   __device__ __forceinline__ void finish(int, int) {}
 };
+
+
+// ---- radix-31 inverse butterfly in three rolled groups of five output pairs --------------------------------------
+// The fully unrolled conjugate-pair butterfly is ~1100 instructions (17 KB); sixteen unsynchronised warps streaming
+// through it (and the rest of a 62 KB kernel) miss the 32 KB L1.5 instruction cache all the time
+// (profiles/ncu_summary_r2_v1.md: `no_instruction` 1.5 stalled warps per issue).  With the pairs taken in the order of
+// the powers of the primitive root 3, cos(2 pi j_n k_m / 31) = C[(n + m) mod 15]: the 15 x 15 cosine matrix is a
+// circulant (the sine matrix a skew-circulant), so output group q = 0, 1, 2 is the same straight-line code applied to
+// the pair arrays rotated by 5 q places -- 400 instructions executed three times, plus 2 x 60 register moves.
+struct R31 {
+  cpx A[15], B[15];   // a'_n = x[j_n] + x[31 - j_n],  b'_n = sg_n (x[j_n] - x[31 - j_n])
+  cpx x0;
+  // v: spectrum values, y: code-spectrum values (row stride ys); returns the DC output
+  __device__ __forceinline__ cpx prepare(const cpx* v, const cpx* y, int ys) {
+    constexpr int J[15] = SGX_R31_J;
+    constexpr int SG[15] = SGX_R31_SG;
+    x0 = fft::cmulf(v[0], y[0]);
+    cpx dc = x0;
+#pragma unroll
+    for (int n = 0; n < 15; ++n) {
+      const cpx p = fft::cmulf(v[J[n]], y[J[n] * ys]), q = fft::cmulf(v[31 - J[n]], y[(31 - J[n]) * ys]);
+      A[n] = fft::cadd(p, q);
+      B[n] = SG[n] > 0 ? fft::csub(p, q) : fft::csub(q, p);
+      dc = fft::cadd(dc, A[n]);
+    }
+    return dc;
+  }
+  // output pair r of the current group: hi -> row KHI31[5 q + r], lo -> row 31 - KHI31[5 q + r]
+  template <int r>
+  __device__ __forceinline__ void pair(cpx& hi, cpx& lo) const {
+    float cr = x0.x, ci = x0.y, sr = 0.f, si = 0.f;
+#pragma unroll
+    for (int n = 0; n < 15; ++n) {
+      const float c = C31R[(n + r) % 15], s = S31R[n + r];
+      cr = fmaf(A[n].x, c, cr);
+      ci = fmaf(A[n].y, c, ci);
+      sr = fmaf(B[n].x, s, sr);
+      si = fmaf(B[n].y, s, si);
+    }
+    hi = make_float2(cr - si, ci + sr);
+    lo = make_float2(cr + si, ci - sr);
+  }
+  // output pair m = 0..14 from the unrotated arrays (fully unrolled variant: no register moves, 3x the code)
+  template <int m>
+  __device__ __forceinline__ void pair_at(cpx& hi, cpx& lo) const {
+    float cr = x0.x, ci = x0.y, sr = 0.f, si = 0.f;
+#pragma unroll
+    for (int n = 0; n < 15; ++n) {
+      const float c = C31R[(n + m) % 15], s = S31R[n + m];
+      cr = fmaf(A[n].x, c, cr);
+      ci = fmaf(A[n].y, c, ci);
+      sr = fmaf(B[n].x, s, sr);
+      si = fmaf(B[n].y, s, si);
+    }
+    hi = make_float2(cr - si, ci + sr);
+    lo = make_float2(cr + si, ci - sr);
+  }
+  __device__ __forceinline__ void rotate() {   // A_n <- A_(n-5 mod 15);  B_n <- B_(n-5), antiperiodic
+    cpx tA[15], tB[15];
+#pragma unroll
+    for (int n = 0; n < 15; ++n) {
+      tA[n] = A[(n + 10) % 15];
+      tB[n] = n < 5 ? make_float2(-B[n + 10].x, -B[n + 10].y) : B[n - 5];
+    }
+#pragma unroll
+    for (int n = 0; n < 15; ++n) { A[n] = tA[n]; B[n] = tB[n]; }
+  }
+};
+
+
+// ---- forward transform into the residue order ---------------------------------------------------------------------
+// X[k] = sum_n x[n] exp(-2 pi i n k / N) with the input taken in the Ruritanian order n = (n1 N/31 + n2 N/7 + n3 N/16 +
+// n4 N/11) mod N: the 4-D output coordinates are then the residues (k mod 31, k mod 7, k mod 16, k mod 11), i.e. exactly
+// the storage order the search kernel reads -- no permutation pass, no scattered stores.  Same two passes and slices as
+// the search kernel; one CTA per transform, `Pro::load(n)` supplies sample n (int8 x carrier NCO, or a code table row).
+struct ForwardArgs {
+  cpx* scratch;      // [gridDim.x][NB][SROW]
+  cpx* out;          // [batch][N], residue order
+  long long out_stride;
+  float scale;
+  int conj;
+  int nbatch;
+};
+
+template <class Pro, int P1, int P2, int P3, int P4, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) pfa_forward_kernel(ForwardArgs a, Pro pro0) {
+  typedef Shape<P1, P2, P3, P4> S;
+  static_assert(P1 == 31, "stage 1 is the radix-31 butterfly");
+  constexpr int NA = S::NA, NB = S::NB, N = S::N, SROW = S::SROW;
+  constexpr int Q1 = N / P1, Q2 = N / P2, Q3 = N / P3, Q4 = N / P4;
+  constexpr int CA = S::CA, CB = S::CB, KA = 32 / CA, KB = 32 / CB;
+  SGX_DYN_SMEM(smem);
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  cpx* X = reinterpret_cast<cpx*>(smem) + (size_t)w * S::WARP_TILE;
+  cpx* scr = a.scratch + (size_t)blockIdx.x * NB * SROW;
+  const int ja = lane & (CA - 1), ka = lane / CA;
+  const int jb = lane & (CB - 1), kb = lane / CB;
+#pragma unroll 1
+  for (int item = blockIdx.x; item < a.nbatch; item += gridDim.x) {
+    Pro pro = pro0;
+    pro.prepare(item);
+    // pass A: DFT over (n1, n2); slice = CA values of nB = n3*P4 + n4
+#pragma unroll 1
+    for (int sa = w; sa < S::NSA; sa += WARPS) {
+      if (ka < P2) {
+        const int nB = sa * CA + ja;
+        int n = (ka * Q2 + (nB / P4) * Q3 + (nB % P4) * Q4) % N;
+        cpx v[P1];
+#pragma unroll
+        for (int n1 = 0; n1 < P1; ++n1) {
+          v[n1] = pro.load(n);
+          n += Q1;
+          if (n >= N) n -= N;
+        }
+        fft::Dft<P1, false>::run(v);
+        cpx* x = X + ka * CA + ja;
+#pragma unroll
+        for (int k1 = 0; k1 < P1; ++k1) x[k1 * (P2 * CA)] = v[k1];
+      }
+      __syncwarp();
+#pragma unroll 1
+      for (int k1 = ka; k1 < P1; k1 += KA) {
+        cpx u[P2];
+        cpx* rp = X + (k1 * P2) * CA + ja;
+#pragma unroll
+        for (int n2 = 0; n2 < P2; ++n2) u[n2] = rp[n2 * CA];
+        fft::Dft<P2, false>::run(u);
+#pragma unroll
+        for (int k2 = 0; k2 < P2; ++k2) rp[k2 * CA] = u[k2];
+      }
+      __syncwarp();
+      {
+        cpx* dst = scr + (size_t)(sa * CA + (lane & 1) * 2) * SROW;
+#pragma unroll 1
+        for (int c = lane >> 1; c < NA; c += 16) {
+          const float4 x = *reinterpret_cast<const float4*>(X + c * CA + (lane & 1) * 2);
+          __stcg(dst + c, make_float2(x.x, x.y));
+          __stcg(dst + SROW + c, make_float2(x.z, x.w));
+        }
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+    // pass B: DFT over (n4, n3); slice = CB values of kA = k1*P2 + k2; output X[kA][k3*P4 + k4]
+    cpx* out = a.out + (long long)item * a.out_stride;
+#pragma unroll 1
+    for (int sb = w; sb < S::NSB; sb += WARPS) {
+      const int kA = sb * CB + jb;
+      const bool valid = kA < NA;
+#pragma unroll 1
+      for (int n3 = kb; n3 < P3; n3 += KB) {
+        cpx u[P4];
+        const cpx* p = scr + (size_t)(n3 * P4) * SROW + (valid ? kA : 0);
+#pragma unroll
+        for (int n4 = 0; n4 < P4; ++n4) u[n4] = __ldcg(p + (size_t)n4 * SROW);
+        fft::Dft<P4, false>::run(u);
+        cpx* rp = X + (n3 * P4) * CB + jb;
+#pragma unroll
+        for (int k4 = 0; k4 < P4; ++k4) rp[k4 * CB] = u[k4];
+      }
+      __syncwarp();
+#pragma unroll 1
+      for (int k4 = kb; k4 < P4; k4 += KB) {
+        cpx u[P3];
+        const cpx* rp = X + k4 * CB + jb;
+#pragma unroll
+        for (int n3 = 0; n3 < P3; ++n3) u[n3] = rp[(n3 * P4) * CB];
+        fft::Dft<P3, false>::run(u);
+        if (valid) {
+          cpx* o = out + (size_t)kA * NB + k4;
+#pragma unroll
+          for (int k3 = 0; k3 < P3; ++k3)
+            o[k3 * P4] = make_float2(u[k3].x * a.scale, a.conj ? -u[k3].y * a.scale : u[k3].y * a.scale);
+        }
+      }
+      __syncwarp();
+    }
+    __syncthreads();   // the scratch is rewritten by the next transform
+  }
+}
+
+// `batch` forward transforms of N = SearchShape::N points into out[batch][N] (residue order).  Grows `scratch`.
+template <class Pro>
+inline int launch_forward(Pro pro, int batch, cpx* out, float scale, int conj, DevBuf& scratch, cudaStream_t s) {
+  typedef Shape<31, 7, 16, 11> S;
+  if (batch <= 0) return SGX_OK;
+  constexpr int WARPS = 4, MINB = 4;
+  auto kfn = pfa_forward_kernel<Pro, 31, 7, 16, 11, WARPS, MINB>;
+  const size_t smem = S::smem_per_warp * WARPS;
+  SGX_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, n_sm = 0, occ = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  if (n_sm <= 0) n_sm = 148;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, WARPS * 32, smem) != cudaSuccess || occ < 1) occ = 1;
+  long long grid = (long long)n_sm * occ;
+  if (grid > batch) grid = batch;
+  if (scratch.reserve(S::scratch_per_cta * (size_t)grid)) return fail(SGX_ERR_CUDA, "cudaMalloc", "forward scratch");
+  ForwardArgs a;
+  a.scratch = scratch.as<cpx>(); a.out = out; a.out_stride = S::N; a.scale = scale; a.conj = conj; a.nbatch = batch;
+  SGX_COUNTED_LAUNCH(kfn, dim3((unsigned)grid), dim3(WARPS * 32), smem, s, a, pro);
+  SGX_CUDA(cudaGetLastError());
+  return SGX_OK;
+}
 
 typedef Shape<31, 7, 16, 11> SearchShape;   // 38 192 = 31 * 7 * 16 * 11 (fs = 38.192 MHz, 1 ms)
 
