@@ -13,19 +13,25 @@
 // Device formulation (DESIGN.md section "K5"):
 //  * the block of int8 samples is staged in shared memory one period ahead (TMA 1-D bulk copy
 //    completing on an mbarrier, or 16-byte cp.async), double buffered;
-//  * each thread owns a contiguous run of 16-sample groups.  The carrier is e^{j theta_i} =
-//    rot_g * w^k (k = 0..15): sixteen per-period twiddles w^k live in registers, rot_g advances by
-//    w^16 per group, so a sample costs one byte->float conversion and two FMAs;
-//  * the replicas are piecewise constant (one chip = 37.3 samples): every thread walks the chip
-//    boundaries ("events") of E, P and L inside its run.  An event index is predicted in float64
-//    from the reference's own linspace parameters and, when the prediction is within 1e-6 of an
-//    integer, settled by evaluating the reference's expression fl(fl(i*step)+start) exactly, so
-//    the sample->chip assignment equals ceil(tcode) of the reference for every sample;
-//  * a group is summed in two halves split at the (at most one) event position, the halves are
-//    rotated once and added with the code signs -> 6 running sums per thread, warp shuffle,
-//    one shared-memory exchange;
-//  * thread 0 then runs T8/T9/T5/T3 in float64 with separately rounded operations (compiled with
-//    -fmad=false) exactly in the reference's order and publishes the next period's parameters.
+//  * the replicas are piecewise constant and, with E/L at +-0.5 chip, change only at the 2 046 half-chip
+//    thresholds of a period: every thread owns 8 consecutive half-chip segments (~18.7 samples each).  A
+//    boundary is predicted in Q40 fixed point from the reference's own linspace parameters and, when the
+//    prediction is within 1e-6 of a sample instant, settled by evaluating the reference's expression
+//    fl(fl(i*step)+start) exactly (settle_boundary), so the sample->chip assignment equals ceil(tcode) of the
+//    reference for every sample;
+//  * default (exact) variant: the carrier twiddles w^k of a segment are quantised once per period to Q38
+//    (five signed base-256 digits, built by the carrier thread's warp in float64), a segment sum is 10 dp4a per
+//    four samples with exact int32 accumulation, the digits are recombined exactly and rotated by the segment's
+//    start rotor in float64; the three code values enter as sign-bit flips.  Agreement with the reference's
+//    float64 loop: ~2e-11 of full scale, which keeps absoluteSample identical over 37 000 ms.
+//    `SGX_TRK_KERNEL=segments` selects a float32 version of the same segmentation, `groups` the aligned
+//    16-sample-group formulation (any correlator spacing; used automatically when dllCorrelatorSpacing != 0.5);
+//  * six float64 sums per thread -> warp shuffle -> one shared-memory exchange;
+//  * thread 0 (code loop: T9, T5, T3/T4 of the next period) and thread 32 (carrier loop: T6 carry, T8, T6 of the
+//    next period) then run the loop filters in float64 with separately rounded operations (compiled with
+//    -fmad=false) exactly in the reference's order, and the carrier thread's warp rebuilds the twiddle tables.
+//  * host recordings are streamed in chunks (pause/resume through TrackState); files through two pinned staging
+//    buffers (sgx_track_file).
 #include <vector>
 #include <fcntl.h>
 #include <sys/stat.h>
