@@ -769,7 +769,7 @@ extern "C" int sgx_acquire(const int8_t* sig, int64_t rec_stride, int64_t n_samp
       fine::Args fa;
       fa.sig = d_sig; fa.rec_stride = stride; fa.sums = (const long long*)a.sums.p; fa.n_samples = (long long)n_samples;
       fa.chips = a.chips.as<int8_t>(); fa.idx = a.fidx.as<unsigned short>(); fa.items = a.fitems.as<FineItem>();
-      fa.nvalid = a.nvalid; fa.lo = 4; fa.hi = uniq - 5;
+      fa.nvalid = a.nvalid; fa.n_items = 0; fa.lo = 4; fa.hi = uniq - 5;
       fa.w2048 = nullptr; fa.wlo = nullptr; fa.y = nullptr; fa.partial = nullptr; fa.stripped = nullptr; fa.strip_stride = 0;
       rc = fine::run(fa, nf, a.findex.as<int>(), s);
       if (rc) return rc;

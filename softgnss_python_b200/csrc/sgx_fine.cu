@@ -67,15 +67,6 @@ __device__ __forceinline__ void dif_stage(cpx* x, const cpx* __restrict__ W, int
   }
 }
 
-__device__ __forceinline__ void fft2048_inplace(cpx* x, const cpx* W, int tid) {
-  dif_stage<16, 2048, false>(x, W, tid);
-  __syncthreads();
-  dif_stage<16, 128, false>(x, W, tid);
-  __syncthreads();
-  dif_stage<8, 8, false>(x, W, tid);
-  __syncthreads();
-}
-
 // (x - mean) * code for the nvalid samples of every detection, zero-padded to whole rows of 2048 (acquisition.py:177)
 __global__ void strip_kernel(Args a, int padded) {
   const FineItem it = a.items[blockIdx.y];
@@ -87,26 +78,54 @@ __global__ void strip_kernel(Args a, int padded) {
     out[n] = n < a.nvalid ? ((float)sig[n] - mean) * (float)chips[a.idx[n]] : 0.f;
 }
 
-// step 1: blockIdx.x = column tile (2 C real columns), blockIdx.y = detection
+// step 1: persistent CTAs walk the (column tile of 2 C real columns, detection) pairs
 __global__ void __launch_bounds__(NT, 2) fine_cols_kernel(Args a) {
   SGX_DYN_SMEM(smem);
   cpx* x = reinterpret_cast<cpx*>(smem);
   cpx* W = x + R * CP;
-  const int tid = threadIdx.x, tile = blockIdx.x;
-  for (int i = tid; i < R; i += NT) W[i] = a.w2048[i];
-  const int n_rows = (a.nvalid + R - 1) / R;    // rows n2 that hold samples
+  const int tid = threadIdx.x;
+  for (int i = tid; i < R; i += NT) W[i] = a.w2048[i];        // once per (persistent) CTA
+  const int n_rows = (a.nvalid + R - 1) / R;    // rows n2 that hold samples (187 of 2048: the rest is zero padding)
+  constexpr int COL_TILES = R / (2 * C);
+#pragma unroll 1
+  for (int work = blockIdx.x; work < COL_TILES * a.n_items; work += gridDim.x) {
+  const int tile = work % COL_TILES, item = work / COL_TILES;
   // code-stripped samples of this detection (strip_kernel), padded with zeros to whole rows: two reals = one element
-  const cpx* xs = reinterpret_cast<const cpx*>(a.stripped + (long long)blockIdx.y * a.strip_stride) + tile * C;
-  for (int idx = tid; idx < R * C; idx += NT) {
-    const int c = idx % C, n2 = idx / C;
-    x[at(n2, c)] = n2 < n_rows ? __ldg(xs + (long long)n2 * (R / 2) + c) : make_float2(0.f, 0.f);
+  const cpx* xs = reinterpret_cast<const cpx*>(a.stripped + (long long)item * a.strip_stride) + tile * C;
+  // Pruned first stage (radix 16 over rows j + 128 u): only u = 0 and u = 1 can be non-zero, so
+  //   y[u'] = (v0 + w_16^u' v1) w_2048^(j u') = v0 W[j u'] + v1 W[(128 + j) u']
+  // straight from global memory into the tile (requires n_rows <= 256; it is 187).
+  __syncthreads();   // the twiddle table is complete
+  for (int idx = tid; idx < 128 * C; idx += NT) {
+    const int c = idx % C, j = idx / C;
+    const cpx v0 = j < n_rows ? __ldg(xs + (long long)j * (R / 2) + c) : make_float2(0.f, 0.f);
+    const cpx v1 = j + 128 < n_rows ? __ldg(xs + (long long)(j + 128) * (R / 2) + c) : make_float2(0.f, 0.f);
+    x[at(j, c)] = fft::cadd(v0, v1);
+#pragma unroll
+    for (int u = 1; u < 16; ++u) {
+      const cpx w0 = W[(j * u) & (R - 1)], w1 = W[((128 + j) * u) & (R - 1)];
+      x[at(j + 128 * u, c)] = fft::cadd(fft::cmulf(v0, w0), fft::cmulf(v1, w1));
+    }
   }
   __syncthreads();
-  fft2048_inplace(x, W, tid);
-  // separate the two real columns of every complex column, apply w_N^(n1 k2), store Y[k2][n1]
-  cpx* out = a.y + ((long long)blockIdx.y * ROWS_KEPT) * R + tile * 2 * C;
-  for (int idx = tid; idx < ROWS_KEPT * C; idx += NT) {
-    const int c = idx % C, k2 = idx / C;
+  dif_stage<16, 128, false>(x, W, tid);
+  __syncthreads();
+  dif_stage<8, 8, false>(x, W, tid);
+  __syncthreads();
+  // separate the two real columns of every complex column, apply w_N^(n1 k2), store Y[k2][n1].  Items are walked in
+  // tile-position order (k2 = ka + 16 kb + 256 kc sits at row (16 ka + kb) 8 + kc): a half-warp reads 4 consecutive
+  // rows x 4 columns, conflict-free; k2 = 1024 (position 4) is done by the first C threads.
+  cpx* out = a.y + ((long long)item * ROWS_KEPT) * R + tile * 2 * C;
+  for (int idx = tid; idx < (R / 2) * C + C; idx += NT) {
+    int c, k2;
+    if (idx < (R / 2) * C) {
+      c = idx & (C - 1);
+      const int kc = (idx >> 2) & 3, g = idx >> 4;
+      k2 = (g >> 4) + 16 * (g & 15) + 256 * kc;
+    } else {
+      c = idx - (R / 2) * C;
+      k2 = R / 2;
+    }
     const cpx zp = x[at(digit_rev(k2), c)], zm = x[at(digit_rev((R - k2) & (R - 1)), c)];
     cpx ya = make_float2(zp.x + zm.x, zp.y - zm.y);           // 2 X_a[k2]
     cpx yb = make_float2(zp.y + zm.y, zm.x - zp.x);           // 2 X_b[k2]
@@ -115,6 +134,8 @@ __global__ void __launch_bounds__(NT, 2) fine_cols_kernel(Args a) {
     ya = fft::cmulf(ya, fft::cmulf(W[ma >> 11], __ldg(a.wlo + (ma & (R - 1)))));
     yb = fft::cmulf(yb, fft::cmulf(W[mb >> 11], __ldg(a.wlo + (mb & (R - 1)))));
     *reinterpret_cast<float4*>(out + (long long)k2 * R + 2 * c) = make_float4(ya.x, ya.y, yb.x, yb.y);
+  }
+  __syncthreads();   // the tile is rewritten by the next work item
   }
 }
 
@@ -215,6 +236,8 @@ static Scratch g_fine;
 
 int run(Args a, int n_items, int* d_index, cudaStream_t s) {
   if (n_items <= 0) return SGX_OK;
+  static_assert(C == 4, "index arithmetic of the output phase of step 1");
+  if ((a.nvalid + R - 1) / R > 256) return fail(SGX_ERR_ARG, "fine search", "more than 256 non-zero rows");
   Scratch& g = g_fine;
   if (!g.tables) {
     if (g.w2048.reserve(sizeof(cpx) * R) || g.wlo.reserve(sizeof(cpx) * R)) return fail(SGX_ERR_CUDA, "cudaMalloc", "fine tables");
@@ -245,7 +268,15 @@ int run(Args a, int n_items, int* d_index, cudaStream_t s) {
     const int cnt = n_items - i0 < chunk ? n_items - i0 : (int)chunk;
     a.items = items + i0;
     SGX_COUNTED_LAUNCH(strip_kernel, dim3(64, cnt), dim3(256), 0, s, a, padded);
-    SGX_COUNTED_LAUNCH(fine_cols_kernel, dim3(col_tiles, cnt), dim3(NT), smem_cols, s, a);
+    a.n_items = cnt;
+    {
+      int dev = 0, n_sm = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+      long long grid = 2LL * (n_sm > 0 ? n_sm : 148);
+      if (grid > (long long)col_tiles * cnt) grid = (long long)col_tiles * cnt;
+      SGX_COUNTED_LAUNCH(fine_cols_kernel, dim3((unsigned)grid), dim3(NT), smem_cols, s, a);
+    }
     SGX_COUNTED_LAUNCH(fine_rows_kernel, dim3(row_tiles, cnt), dim3(NT), smem, s, a);
     SGX_COUNTED_LAUNCH(fine_argmax_kernel, dim3(cnt), dim3(128), 0, s, a.partial, row_tiles, d_index + i0);
   }

@@ -17,6 +17,7 @@ struct Args {
   const unsigned short* idx;     // [nvalid] chip index of acquisition.py:172-174
   const FineItem* items;         // detections: recording, PRN, code phase
   int nvalid;
+  int n_items;                   // detections of this launch (persistent step-1 kernel)
   int lo, hi;                    // candidate bins lo <= k < hi; the key index is k - lo (slice-relative, :186-187)
   const cpx* w2048;              // [2048] exp(-2 pi i q / 2048)
   const cpx* wlo;                // [2048] exp(-2 pi i q / 2^22)
