@@ -338,6 +338,8 @@ static int launch_search_t(SearchArgs args, DevBuf& scratch, cudaStream_t s) {
     case 141: return launch_cfg<14, 1, MASKED>(args, scratch, s);
     case 161: return launch_cfg<16, 1, MASKED>(args, scratch, s);
     case 62: return launch_cfg<6, 2, MASKED>(args, scratch, s);
+    case 153: return launch_cfg<5, 3, MASKED, true>(args, scratch, s);    // 15 warps per SM, 136 registers
+    case 144: return launch_cfg<4, 4, MASKED, true>(args, scratch, s);    // 16 warps per SM, 128 registers
     case 43: return launch_cfg<4, 3, MASKED>(args, scratch, s);           // rolled radix-31 groups (21.4 ms per batch)
     default: return launch_cfg<4, 3, MASKED, true>(args, scratch, s);     // radix-31 butterfly fully unrolled (21.2 ms)
   }

@@ -1001,7 +1001,7 @@ static int track_core(const int8_t* rec, int64_t rec_stride, const int64_t* rec_
     stride = (max_len + 15) & ~15LL;
     if (g_trk.rec.reserve((size_t)stride * n_recordings + 16)) return fail(SGX_ERR_CUDA, "cudaMalloc", "recording");
     d_rec = g_trk.rec.as<int8_t>();
-  } else if ((rec_stride & 15) || ((uintptr_t)rec & 15)) {
+  } else if (((rec_stride & 15) && n_recordings > 1) || ((uintptr_t)rec & 15)) {   // (one recording: the stride is not used)
     return fail(SGX_ERR_ARG, "sgx_track", "device recordings must be 16-byte aligned with a stride multiple of 16");
   }
   if (g_trk.len.reserve(sizeof(long long) * n_recordings) || g_trk.ch.reserve(sizeof(sgx_channel) * nch) ||

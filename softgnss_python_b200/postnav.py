@@ -72,14 +72,13 @@ def navBitsBin(bits_row):
 def calculatePseudoranges(trackResults, msOfTheSignal, channelList, settings):
     """postNavigation.py:27-72 for one measurement epoch (function-style form of the reference method)."""
     n_ch = settings.numberOfChannels
-    ms = len(trackResults[0].absoluteSample)
-    trk = np.zeros((1, n_ch, len(_native.TRACK_FIELDS), ms))
-    for c in range(min(n_ch, len(trackResults))):
-        trk[0, c, 0] = trackResults[c].absoluteSample
+    # the reference calls this once per measurement epoch: hand the device only the one sample per channel it reads
+    # (a [1, C, 13, 1] view of the tracking result, epoch index 0), not the whole 30 MB result
+    trk = np.zeros((1, n_ch, len(_native.TRACK_FIELDS), 1))
     idx = np.zeros((1, 1, n_ch), dtype=np.int32)
     act = np.zeros((1, 1, n_ch), dtype=np.uint8)
     for c in channelList:
-        idx[0, 0, c] = int(msOfTheSignal[c])
+        trk[0, c, 0, 0] = trackResults[c].absoluteSample[int(msOfTheSignal[c])]
         act[0, 0, c] = 1
     return pseudoranges_batch(trk, idx, act, settings)[0, 0]
 

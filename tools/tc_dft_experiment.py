@@ -30,6 +30,11 @@ def split16(x, dt):
     return hi, lo
 
 
+def mm32(a, b):
+    """fp16/bf16 operands, fp32 accumulator AND fp32 output (what a TMEM accumulator read back with tcgen05.ld gives)."""
+    return torch.mm(a, b, out_dtype=torch.float32)
+
+
 def timed(fn, reps=20):
     for _ in range(3):
         fn()
@@ -47,16 +52,24 @@ def timed(fn, reps=20):
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 1676          # transforms per launch of the CUDA-core pass (ncu_summary_r1_v5)
     dev = "cuda"
+    torch.backends.cuda.matmul.allow_fp16_reduced_precision_reduction = False      # fp32 accumulation, as a TMEM accumulator
+    torch.backends.cuda.matmul.allow_bf16_reduced_precision_reduction = False
     rng = np.random.default_rng(1)
     for name, p, cols_per_tr in (("pass217", 217, 176), ("stage31", 31, 1232)):
-        W64 = dft_real(p)
-        n = cols_per_tr * B
-        X64 = rng.standard_normal((2 * p, min(n, 65536)))      # error check on a slice
+        # zero-padded to multiples of 64 / 128: with the raw 434 (or 62) cuBLAS falls back to an sm_80-style mma.sync kernel
+        # (cutlass_80_tensorop_s16816gemm, align2); padded, it picks its sm_100 (tcgen05) kernels
+        q = (2 * p + 63) // 64 * 64
+        W64 = np.zeros((q, q))
+        W64[:2 * p, :2 * p] = dft_real(p)
+        n = (cols_per_tr * B + 127) // 128 * 128
+        X64 = np.zeros((q, min(n, 65536)))
+        X64[:2 * p] = rng.standard_normal((2 * p, X64.shape[1]))      # error check on a slice
         Y64 = W64 @ X64
         W = torch.tensor(W64, dtype=torch.float32, device=dev)
-        X = torch.randn((2 * p, n), dtype=torch.float32, device=dev)
+        X = torch.randn((q, n), dtype=torch.float32, device=dev)
+        X[2 * p:] = 0
         X[:, :X64.shape[1]] = torch.tensor(X64, dtype=torch.float32, device=dev)
-        flop = 2.0 * (2 * p) * (2 * p) * n
+        flop = 2.0 * (2 * p) * (2 * p) * cols_per_tr * B              # useful work (the padding is not counted)
         res = []
         # fp32 on the CUDA cores (cuBLAS sgemm), for scale
         torch.backends.cuda.matmul.allow_tf32 = False
@@ -70,18 +83,18 @@ def main():
             sc = 1.0 / 8.0                                       # keep |x| well inside the fp16 range
             Wh, Wl = split16(W, dt)
             Xh, Xl = split16(X * sc, dt)
-            ms, Y = timed(lambda: (Wh @ Xh).float() / sc)
+            ms, Y = timed(lambda: mm32(Wh, Xh) / sc)
             res.append((nm + " x1", 1, ms, Y))
 
             def three():
-                acc = torch.matmul(Wh, Xh).float()
-                acc += torch.matmul(Wh, Xl).float()
-                acc += torch.matmul(Wl, Xh).float()
+                acc = mm32(Wh, Xh)
+                acc += mm32(Wh, Xl)
+                acc += mm32(Wl, Xh)
                 return acc / sc
             ms, Y = timed(three)
             res.append((nm + " split x3 (incl. fp32 adds of the three products)", 3, ms, Y))
             # the three products alone (what a fused kernel accumulating in TMEM would pay)
-            ms, _ = timed(lambda: (torch.matmul(Wh, Xh), torch.matmul(Wh, Xl), torch.matmul(Wl, Xh)))
+            ms, _ = timed(lambda: (mm32(Wh, Xh), mm32(Wh, Xl), mm32(Wl, Xh)))
             res.append((nm + " split x3 (GEMMs only)", 3, ms, Y))
         for label, terms, ms, Y in res:
             err = float(np.abs(Y[:, :X64.shape[1]].double().cpu().numpy() - Y64).max() / np.abs(Y64).max())
