@@ -606,6 +606,26 @@ inline bool plan_passes(int N, int maxR, int groups[4][MAX_SUB], int gcnt[4], in
     if (best > 0) {
       for (int g = 0; g < np; ++g) gcnt[g] = 0;
       for (int i = 0; i < cnt; ++i) groups[bestAssign[i]][gcnt[bestAssign[i]]++] = rad[i];
+      if (np >= 3) {
+        // Pass order is free in a Stockham transform.  The persistent pass kernels need the twiddle rows of a tile not to
+        // wrap (Ls % 16 == 0, async_ok below): put a pass whose radix is a multiple of 16 first, then every later Ls is one
+        // too (381 920 = 62 x 77 x 80 ran its middle pass through the synchronous kernel; as 80 x 62 x 77 it does not).
+        int first = -1;
+        long long fprod = 0;
+        for (int g = 0; g < np; ++g) {
+          long long prod = 1;
+          for (int i = 0; i < gcnt[g]; ++i) prod *= groups[g][i];
+          if (prod % 16 == 0 && prod > fprod) { first = g; fprod = prod; }
+        }
+        if (first > 0) {
+          int tmp[MAX_SUB];
+          const int tc = gcnt[first];
+          memcpy(tmp, groups[first], sizeof(tmp));
+          for (int g = first; g > 0; --g) { memcpy(groups[g], groups[g - 1], sizeof(tmp)); gcnt[g] = gcnt[g - 1]; }
+          memcpy(groups[0], tmp, sizeof(tmp));
+          gcnt[0] = tc;
+        }
+      }
       return true;
     }
   }
