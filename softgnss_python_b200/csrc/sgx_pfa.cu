@@ -15,45 +15,37 @@ __device__ __forceinline__ void pass_b(const cpx* scr, cpx* X, int w, int lane, 
   constexpr int NA = S::NA, N = S::N, SROW = S::SROW, CB = S::CB, KB = 32 / CB;
   constexpr int Q1 = N / S::p1, Q2 = N / P2, Q3 = N / P3, Q4 = N / P4;
   const int jb = lane & (CB - 1), kb = lane / CB;
+  // Two register sets in flight: within a slice the loads of round r+2 travel while round r is computed, and the first
+  // TWO rounds of the next slice travel during this slice's second stage (the scratch of 444 CTAs does not fit the L2:
+  // many of these loads come from HBM).
+  static_assert(P3 / KB == 4, "four rounds per slice");
   cpx ua[P4], ub[P4];
-  {  // first round of the first slice
-    const int tA = w * CB + jb;
-    const cpx* p = scr + (size_t)(kb * P4) * SROW + (tA < NA ? tA : 0);
+  auto load_round = [&](cpx* u, int sb, int r) {
+    const int tA = sb * CB + jb;
+    const cpx* p = scr + (size_t)((kb + KB * r) * P4) * SROW + (tA < NA ? tA : 0);
 #pragma unroll
-    for (int k4 = 0; k4 < P4; ++k4) ua[k4] = __ldcg(p + (size_t)k4 * SROW);
-  }
+    for (int k4 = 0; k4 < P4; ++k4) u[k4] = __ldcg(p + (size_t)k4 * SROW);
+  };
+  auto do_round = [&](cpx* u, int r) {
+    fft::Dft<P4, true>::run(u);
+    cpx* rp = X + ((kb + KB * r) * P4) * CB + jb;
+#pragma unroll
+    for (int t4 = 0; t4 < P4; ++t4) rp[t4 * CB] = u[t4];
+  };
+  if (w < S::NSB) { load_round(ua, w, 0); load_round(ub, w, 1); }
 #pragma unroll 1
   for (int sb = w; sb < S::NSB; sb += WARPS) {
     const int tA = sb * CB + jb;
     const bool valid = tA < NA;
-    // stage 1 (radix P4 over k4): lane (k3 = kb + KB*r, column jb); tile rows k3*P4 + k4 -> k3*P4 + tau4.
-    // Two register sets: the loads of round r+1 are in flight while round r is computed.
-    {
-      const cpx* p = scr + (size_t)(kb * P4) * SROW + (valid ? tA : 0);
-      cpx* rp = X + (kb * P4) * CB + jb;
-#pragma unroll 1
-      for (int r = 0; r < 4; r += 2) {
-#pragma unroll
-        for (int k4 = 0; k4 < P4; ++k4) ub[k4] = __ldcg(p + (size_t)((r + 1) * KB * P4 + k4) * SROW);
-        fft::Dft<P4, true>::run(ua);
-#pragma unroll
-        for (int t4 = 0; t4 < P4; ++t4) rp[(r * KB * P4 + t4) * CB] = ua[t4];
-        if (r + 2 < 4) {
-#pragma unroll
-          for (int k4 = 0; k4 < P4; ++k4) ua[k4] = __ldcg(p + (size_t)((r + 2) * KB * P4 + k4) * SROW);
-        }
-        fft::Dft<P4, true>::run(ub);
-#pragma unroll
-        for (int t4 = 0; t4 < P4; ++t4) rp[((r + 1) * KB * P4 + t4) * CB] = ub[t4];
-      }
-    }
+    // stage 1 (radix P4 over k4): lane (k3 = kb + KB*r, column jb); tile rows k3*P4 + k4 -> k3*P4 + tau4
+    do_round(ua, 0);
+    load_round(ua, sb, 2);
+    do_round(ub, 1);
+    load_round(ub, sb, 3);
+    do_round(ua, 2);
+    do_round(ub, 3);
     __syncwarp();
-    if (sb + WARPS < S::NSB) {   // first round of the next slice travels during stage 2
-      const int tn = (sb + WARPS) * CB + jb;
-      const cpx* p = scr + (size_t)(kb * P4) * SROW + (tn < NA ? tn : 0);
-#pragma unroll
-      for (int k4 = 0; k4 < P4; ++k4) ua[k4] = __ldcg(p + (size_t)k4 * SROW);
-    }
+    if (sb + WARPS < S::NSB) { load_round(ua, sb + WARPS, 0); load_round(ub, sb + WARPS, 1); }
     // stage 2 (radix P3 over k3): lane (tau4 = kb + KB*r, column jb); outputs stay in registers
     const int baseA = valid ? ((tA / P2) * Q1 + (tA % P2) * Q2) % N : 0;
 #pragma unroll 1
@@ -228,10 +220,17 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pfa_search_kernel(SearchArgs
       {
         cpx* dst = scr + (size_t)(sa * CA + (lane & 1) * 2) * SROW;
 #pragma unroll 1
-        for (int c = lane >> 1; c < NA; c += 16) {
+        for (int c = lane >> 1; c < NA; c += 32) {      // two rows per iteration: both loads before the four stores
           const float4 x = *reinterpret_cast<const float4*>(X + c * CA + (lane & 1) * 2);
+          const bool second = c + 16 < NA;
+          float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (second) y = *reinterpret_cast<const float4*>(X + (c + 16) * CA + (lane & 1) * 2);
           __stcg(dst + c, make_float2(x.x, x.y));
           __stcg(dst + SROW + c, make_float2(x.z, x.w));
+          if (second) {
+            __stcg(dst + c + 16, make_float2(y.x, y.y));
+            __stcg(dst + SROW + c + 16, make_float2(y.z, y.w));
+          }
         }
       }
       __syncwarp();
