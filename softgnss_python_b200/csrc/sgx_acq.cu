@@ -592,6 +592,46 @@ static int ensure_plan(const sgx_settings* st, const int8_t* ca_table, const int
 
 using namespace sgx;
 
+// SGX_ACQ_PROF=1: CUDA events at the stage boundaries of one sgx_acquire call, printed (ms on the stream, and the host
+// wall clock of the call) when the call returns.  Developer aid; off by default (no events are created).
+struct StageProf {
+  static constexpr int MAXE = 12;
+  cudaStream_t s;
+  bool on;
+  int n = 0;
+  cudaEvent_t ev[MAXE];
+  const char* name[MAXE];
+  double t0 = 0;
+  static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+  explicit StageProf(cudaStream_t st) : s(st) {
+    static const bool env = getenv("SGX_ACQ_PROF") != nullptr;
+    on = env;
+    if (on) { t0 = now(); mark("start"); }
+  }
+  void mark(const char* what) {
+    if (!on || n >= MAXE) return;
+    cudaEventCreate(&ev[n]);
+    cudaEventRecord(ev[n], s);
+    name[n++] = what;
+  }
+  ~StageProf() {
+    if (!on) return;
+    cudaStreamSynchronize(s);
+    const double wall = now() - t0;
+    fprintf(stderr, "[sgx acq prof]");
+    for (int i = 1; i < n; ++i) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+      fprintf(stderr, " %s %.3f", name[i], ms);
+    }
+    float tot = 0;
+    if (n > 1) cudaEventElapsedTime(&tot, ev[0], ev[n - 1]);
+    fprintf(stderr, " | stream %.3f ms, host wall %.3f ms\n", tot, wall);
+    for (int i = 0; i < n; ++i) cudaEventDestroy(ev[i]);
+  }
+};
+
+
 extern "C" int sgx_acquire(const int8_t* sig, int64_t rec_stride, int64_t n_samples, int32_t n_recordings,
                            const sgx_settings* st, const int8_t* ca_table, const int8_t* ca_chips,
                            const uint16_t* fine_idx, int32_t prn_first, int32_t prn_count, double* carrFreq,
@@ -599,6 +639,7 @@ extern "C" int sgx_acquire(const int8_t* sig, int64_t rec_stride, int64_t n_samp
                            void* cuda_stream) {
   if (sgx_device_count() <= 0) return fail(SGX_ERR_NODEV, "sgx_acquire", "no CUDA device");
   SGX_API_GUARD();
+  StageProf prof((cudaStream_t)cuda_stream);
   if (!sig || !st || !ca_table || !ca_chips || !fine_idx || !carrFreq || !codePhase || !peakMetric ||
       n_recordings <= 0 || prn_first < 0 || prn_count <= 0 || prn_first + prn_count > SGX_NUM_PRN)
     return fail(SGX_ERR_ARG, "sgx_acquire", "null pointer or PRN shard outside 0..32");
@@ -667,6 +708,7 @@ extern "C" int sgx_acquire(const int8_t* sig, int64_t rec_stride, int64_t n_samp
     rc = run_fft(a.fwd, false, nspec, ProNco{d_sig, stride, a.cps.as<double>(), nbins, blocks, (int)n, 0.0},
                  fft::StoreCpx{a.spec.as<cpx>(), n, 1.f, 0, nullptr}, a.work0.as<cpx>(), a.work1.as<cpx>(), s);
   if (rc) return rc;
+  prof.mark("sum+forward");
   const int nt_keys = a.pfa ? 1 : nt_last;   // keys per transform: the prime-factor kernel reduces the whole row itself
   // ---- A7: spectrum x code -> IFFT -> |.|^2 -> per-row arg-max ---------------------------------
   if (a.pfa) {
@@ -689,6 +731,7 @@ extern "C" int sgx_acquire(const int8_t* sig, int64_t rec_stride, int64_t n_samp
                    a.work1.as<cpx>(), s);
     if (rc) return rc;
   }
+  prof.mark("search");
   // ---- A8 + A9 -------------------------------------------------------------------------------
   SGX_COUNTED_LAUNCH(select_kernel, dim3(npr), dim3(128), 0, s, a.partial.as<unsigned long long>(), nt_keys, d,
                      a.sel.as<PeakSel>());
@@ -714,6 +757,7 @@ extern "C" int sgx_acquire(const int8_t* sig, int64_t rec_stride, int64_t n_samp
   SGX_COUNTED_LAUNCH(metric_kernel, dim3((npr + 127) / 128), dim3(128), 0, s, a.partial2.as<unsigned long long>(),
                      nt_keys, a.sel.as<PeakSel>(), npr, a.metric.as<double>(), a.cph.as<int>(), a.fbin.as<int>());
   SGX_CUDA(cudaGetLastError());
+  prof.mark("select+second+metric");
   std::vector<int> h_cph_v((size_t)npr * 2);   // host staging is RAII: the SGX_CUDA checks below return early on errors
   int* h_cph = h_cph_v.data();
   int* h_bin = h_cph + npr;
@@ -721,6 +765,7 @@ extern "C" int sgx_acquire(const int8_t* sig, int64_t rec_stride, int64_t n_samp
   SGX_CUDA(cudaMemcpyAsync(h_cph, a.cph.p, sizeof(int) * npr, cudaMemcpyDeviceToHost, s));
   SGX_CUDA(cudaMemcpyAsync(h_bin, a.fbin.p, sizeof(int) * npr, cudaMemcpyDeviceToHost, s));
   SGX_CUDA(cudaStreamSynchronize(s));
+  prof.mark("d2h+sync");
   // ---- decision (acquisition.py:166) and A10 for the detected PRNs ----------------------------
   std::vector<FineItem> items_v(npr);
   std::vector<int> slot_v(npr);
@@ -770,7 +815,7 @@ extern "C" int sgx_acquire(const int8_t* sig, int64_t rec_stride, int64_t n_samp
       fa.sig = d_sig; fa.rec_stride = stride; fa.sums = (const long long*)a.sums.p; fa.n_samples = (long long)n_samples;
       fa.chips = a.chips.as<int8_t>(); fa.idx = a.fidx.as<unsigned short>(); fa.items = a.fitems.as<FineItem>();
       fa.nvalid = a.nvalid; fa.n_items = 0; fa.lo = 4; fa.hi = uniq - 5;
-      fa.w2048 = nullptr; fa.wlo = nullptr; fa.y = nullptr; fa.partial = nullptr; fa.stripped = nullptr; fa.strip_stride = 0;
+      fa.w2048 = nullptr; fa.wlo = nullptr; fa.w128 = nullptr; fa.y = nullptr; fa.partial = nullptr; fa.stripped = nullptr; fa.strip_stride = 0;
       rc = fine::run(fa, nf, a.findex.as<int>(), s);
       if (rc) return rc;
     } else {
@@ -795,10 +840,12 @@ extern "C" int sgx_acquire(const int8_t* sig, int64_t rec_stride, int64_t n_samp
                        nt_f * FINE_SUBS, nf, a.findex.as<int>());
     }
     SGX_CUDA(cudaGetLastError());
+    prof.mark("host decision+fine");
     std::vector<int> h_idx_v(nf);
     int* h_idx = h_idx_v.data();
     SGX_CUDA(cudaMemcpyAsync(h_idx, a.findex.p, sizeof(int) * nf, cudaMemcpyDeviceToHost, s));
     SGX_CUDA(cudaStreamSynchronize(s));
+    prof.mark("d2h+sync");
     for (int f = 0; f < nf; ++f) {
       // fftFreqBins[fftMaxIndex] = arange(uniq) * fs / nfft evaluated at the slice-relative index (:189-191)
       carrFreq[slot[f]] = (double)h_idx[f] * st->samplingFreq / (double)a.nfft;

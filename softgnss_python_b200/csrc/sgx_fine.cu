@@ -32,38 +32,83 @@ constexpr int CP = C;          // row stride; bank conflicts are avoided by the 
 constexpr int NT = 256;
 constexpr int ROWS_KEPT = R / 2 + 1;   // k2 = 0..1024
 
-// Element (row, column c) of a tile lives at row*4 + (c ^ swz(row)).  With 8-byte elements a half-warp's 16 accesses
-// are conflict-free when they fall into 16 different 8-byte bank pairs: the butterfly stages of block sizes 2048 and
-// 128 touch 4 consecutive rows x 4 columns per half-warp (any swizzle works), the last stage rows 8 apart, and the
-// transposed tile load of step 2 sixteen consecutive rows of one column -- both need the swizzle to differ across rows
-// that are 4, 8, 16 and 24 apart.
-__device__ __forceinline__ int at(int row, int c) { return row * CP + (c ^ (((row >> 2) ^ (row >> 4)) & 3)); }
+// Element (row, column c) of a tile lives at (row ^ rs(row))*4 + (c ^ cs(row)), rs = (row >> 3) & 3 (changes only the
+// two low bits of the row), cs = ((row >> 2) ^ (row >> 4)) & 3.  With 8-byte elements a half-warp's 16 accesses are
+// conflict-free when they fall into 16 different 8-byte bank pairs, i.e. 16 different (row' & 3, c') pairs:
+//   * butterfly stages of block sizes 2048 and 128, the pruned first stage and the output walk of step 1: 4 consecutive
+//     rows x 4 columns per half-warp -- rs and cs are constant over them, any swizzle works;
+//   * last stage (radix 8, block 8): rows 8t + u for 4 consecutive t x 4 columns -- the rows agree in their two low
+//     bits, rs = t & 3 separates them (without it: 4-way conflicts on every access of that stage, ncu r2x: 8
+//     wavefronts per request instead of 2, a third of all shared-memory traffic of step 1);
+//   * transposed tile load of step 2: 16 consecutive rows of one column -- cs takes four values over the four groups
+//     of 4 rows, the low bits the other four.
+// Both swizzles together are one 4-bit mask on the linear address: at = (row*4 + c) ^ mask(row), and the mask is
+// linear over GF(2) in the bits of the row.  Hence for a row offset d that shares no bit with row0 (every stage below:
+// row0 = block * L + j, d a multiple of the butterfly distance, or the per-iteration step of a thread)
+//   at(row0 + d, c) = at(row0, c) ^ (4 d ^ mask(d)) = (at(row0, c) ^ low4) + high      (at_off; d a compile-time constant)
+// -- one logic operation per access at most, none when d is a multiple of 64.
+__host__ __device__ constexpr int swz_mask(int row) { return (((row >> 3) & 3) << 2) | (((row >> 2) ^ (row >> 4)) & 3); }
+__device__ __forceinline__ int at(int row, int c) { return (row * CP + c) ^ swz_mask(row); }
+__device__ __forceinline__ int at_off(int a0, int d) {
+  const int k = (d * CP) ^ swz_mask(d);
+  return (a0 ^ (k & 15)) + (k & ~15);
+}
 
 __host__ __device__ constexpr int digit_rev(int k) {   // k = ka + 16 kb + 256 kc  ->  position ka*128 + kb*8 + kc
   return (k & 15) * 128 + ((k >> 4) & 15) * 8 + (k >> 8);
 }
 
-// One decimation-in-frequency stage, in place: blocks of L rows, radix r; twiddles w_L^(j u) = W[(R/L) j u mod R].
+// One decimation-in-frequency stage, in place: blocks of L rows, radix r; twiddles w_L^(j u) = W[(TL/L) j u mod TL],
+// W a table of the TL-th roots of unity.  The block-128 stage uses the compact 128-entry table: in the 2048-entry one
+// its twiddles are 128 bytes apart, every lane of a half-warp in the same bank (ncu r2x: 8 wavefronts per request).
 // WG: the twiddle table is read from global memory through L1 (step 2: three CTAs per SM), else from shared memory.
-template <int r, int L, bool WG>
+template <int r, int L, bool WG, int TL = R>
 __device__ __forceinline__ void dif_stage(cpx* x, const cpx* __restrict__ W, int tid) {
-  constexpr int q = L / r;
-  for (int idx = tid; idx < (R / r) * C; idx += NT) {
-    const int c = idx % C, t = idx / C;
-    const int j = t % q, row0 = (t / q) * L + j;
+  static_assert(TL % L == 0, "table too short for this stage");
+  constexpr int q = L / r, TSTEP = NT / C, ITERS = (R / r) * C / NT;
+  static_assert((R / r) * C % NT == 0 && (q > TSTEP ? q % TSTEP == 0 : TSTEP % q == 0), "whole iterations; constant row step");
+  // item t = t0 + TSTEP*it of column c: j = t % q, row0 = (t / q) * L + j = row0(it = 0) + DSTEP * it, no bits in common
+  constexpr int DSTEP = q > TSTEP ? TSTEP : (TSTEP / q) * L;
+  const int c = tid % C, t0 = tid / C;
+  const int j0 = t0 % q;
+  const int a0 = at((t0 / q) * L + j0, c);
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int j = q > TSTEP ? j0 + TSTEP * it : j0;
     cpx v[r];
 #pragma unroll
-    for (int u = 0; u < r; ++u) v[u] = x[at(row0 + u * q, c)];
+    for (int u = 0; u < r; ++u) v[u] = x[at_off(a0, DSTEP * it + u * q)];
     fft::Dft<r, false>::run(v);
     if (L > r) {
 #pragma unroll
       for (int u = 1; u < r; ++u) {
-        const int wi = ((R / L) * j * u) & (R - 1);
+        const int wi = ((TL / L) * j * u) & (TL - 1);
         v[u] = fft::cmulf(v[u], WG ? __ldg(W + wi) : W[wi]);
       }
     }
 #pragma unroll
-    for (int u = 0; u < r; ++u) x[at(row0 + u * q, c)] = v[u];
+    for (int u = 0; u < r; ++u) x[at_off(a0, DSTEP * it + u * q)] = v[u];
+  }
+}
+
+// v * w_16^u, w_16 = exp(-2 pi i / 16), u a compile-time constant after unrolling (the trivial powers cost no multiply)
+__device__ __forceinline__ cpx mul_w16(cpx v, int u) {
+  constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, H = 0.70710678118654752f;
+  switch (u & 15) {
+    case 0: return v;
+    case 4: return make_float2(v.y, -v.x);
+    case 8: return make_float2(-v.x, -v.y);
+    case 12: return make_float2(-v.y, v.x);
+    case 2: return make_float2((v.x + v.y) * H, (v.y - v.x) * H);
+    case 6: return make_float2((v.y - v.x) * H, -(v.x + v.y) * H);
+    case 10: return make_float2(-(v.x + v.y) * H, (v.x - v.y) * H);
+    case 14: return make_float2((v.x - v.y) * H, (v.x + v.y) * H);
+    default: {
+      // cos / -sin of 2 pi u / 16 for the odd powers
+      const float c = (u == 1 || u == 15) ? C1 : (u == 3 || u == 13) ? S1 : (u == 5 || u == 11) ? -S1 : -C1;
+      const float sn = (u == 1 || u == 7) ? -S1 : (u == 3 || u == 5) ? -C1 : (u == 9 || u == 15) ? S1 : C1;
+      return make_float2(v.x * c - v.y * sn, v.x * sn + v.y * c);
+    }
   }
 }
 
@@ -83,8 +128,10 @@ __global__ void __launch_bounds__(NT, 2) fine_cols_kernel(Args a) {
   SGX_DYN_SMEM(smem);
   cpx* x = reinterpret_cast<cpx*>(smem);
   cpx* W = x + R * CP;
+  cpx* W128 = W + R;
   const int tid = threadIdx.x;
   for (int i = tid; i < R; i += NT) W[i] = a.w2048[i];        // once per (persistent) CTA
+  if (tid < 128) W128[tid] = a.w128[tid];
   const int n_rows = (a.nvalid + R - 1) / R;    // rows n2 that hold samples (187 of 2048: the rest is zero padding)
   constexpr int COL_TILES = R / (2 * C);
 #pragma unroll 1
@@ -93,22 +140,23 @@ __global__ void __launch_bounds__(NT, 2) fine_cols_kernel(Args a) {
   // code-stripped samples of this detection (strip_kernel), padded with zeros to whole rows: two reals = one element
   const cpx* xs = reinterpret_cast<const cpx*>(a.stripped + (long long)item * a.strip_stride) + tile * C;
   // Pruned first stage (radix 16 over rows j + 128 u): only u = 0 and u = 1 can be non-zero, so
-  //   y[u'] = (v0 + w_16^u' v1) w_2048^(j u') = v0 W[j u'] + v1 W[(128 + j) u']
+  //   y[u'] = (v0 + w_16^u' v1) w_2048^(j u')
   // straight from global memory into the tile (requires n_rows <= 256; it is 187).
   __syncthreads();   // the twiddle table is complete
-  for (int idx = tid; idx < 128 * C; idx += NT) {
-    const int c = idx % C, j = idx / C;
+  static_assert(128 * C % NT == 0, "whole iterations");
+#pragma unroll
+  for (int it = 0; it < 128 * C / NT; ++it) {
+    const int c = tid % C, j = tid / C + (NT / C) * it;          // rows j + 128 u: j < 128 shares no bit with 128 u
+    const int a0 = at(tid / C, c);
     const cpx v0 = j < n_rows ? __ldg(xs + (long long)j * (R / 2) + c) : make_float2(0.f, 0.f);
     const cpx v1 = j + 128 < n_rows ? __ldg(xs + (long long)(j + 128) * (R / 2) + c) : make_float2(0.f, 0.f);
-    x[at(j, c)] = fft::cadd(v0, v1);
+    x[at_off(a0, (NT / C) * it)] = fft::cadd(v0, v1);
 #pragma unroll
-    for (int u = 1; u < 16; ++u) {
-      const cpx w0 = W[(j * u) & (R - 1)], w1 = W[((128 + j) * u) & (R - 1)];
-      x[at(j + 128 * u, c)] = fft::cadd(fft::cmulf(v0, w0), fft::cmulf(v1, w1));
-    }
+    for (int u = 1; u < 16; ++u)   // W[(128 + j) u] = w_16^u W[j u]: one table read per output
+      x[at_off(a0, (NT / C) * it + 128 * u)] = fft::cmulf(fft::cadd(v0, mul_w16(v1, u)), W[(j * u) & (R - 1)]);
   }
   __syncthreads();
-  dif_stage<16, 128, false>(x, W, tid);
+  dif_stage<16, 128, false, 128>(x, W128, tid);
   __syncthreads();
   dif_stage<8, 8, false>(x, W, tid);
   __syncthreads();
@@ -148,26 +196,31 @@ __global__ void __launch_bounds__(NT, 3) fine_rows_kernel(Args a) {
   const int tid = threadIdx.x, tile = blockIdx.x;
   const cpx* in = a.y + ((long long)blockIdx.y * ROWS_KEPT + tile * C) * R;
   const int rows = min(C, ROWS_KEPT - tile * C);
+  const int a_t = at(tid, 0);                // at(tid + 256 it, rr) = (a_t + 1024 it) ^ rr
 #pragma unroll 2
-  for (int n1 = tid; n1 < R; n1 += NT) {     // all rows of a column in flight before the first store
+  for (int it = 0; it < R / NT; ++it) {      // all rows of a column in flight before the first store
+    const int n1 = tid + NT * it;
     cpx v[C];
 #pragma unroll
     for (int rr = 0; rr < C; ++rr) v[rr] = rr < rows ? __ldcs(in + (long long)rr * R + n1) : make_float2(0.f, 0.f);
 #pragma unroll
-    for (int rr = 0; rr < C; ++rr) x[at(n1, rr)] = v[rr];
+    for (int rr = 0; rr < C; ++rr) x[(a_t + NT * CP * it) ^ rr] = v[rr];
   }
   __syncthreads();
   dif_stage<16, 2048, true>(x, W, tid);
   __syncthreads();
-  dif_stage<16, 128, true>(x, W, tid);
+  // compact table through L1 as well: one more kilobyte of shared memory would push three CTAs past the 196 KB
+  // carve-out and take 32 KB of L1 away from the twiddles of the first stage (measured: 0.69 -> 0.82 ms per 85 items)
+  dif_stage<16, 128, true, 128>(x, a.w128, tid);
   __syncthreads();
   // last stage (radix 8, no twiddles): outputs stay in registers -> |.|^2, bin index, arg-max
   unsigned long long best = 0ull;
-  for (int idx = tid; idx < (R / 8) * C; idx += NT) {
-    const int c = idx % C, t = idx / C;      // t = ka*16 + kb: the outputs of this butterfly are k1 = ka + 16 kb + 256 u
+  const int a_l = at((tid / C) * 8, tid % C);
+  for (int it = 0; it < (R / 8) * C / NT; ++it) {
+    const int c = tid % C, t = tid / C + (NT / C) * it;   // t = ka*16 + kb: the outputs of this butterfly are k1 = ka + 16 kb + 256 u
     cpx v[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = x[at(t * 8 + u, c)];
+    for (int u = 0; u < 8; ++u) v[u] = x[at_off(a_l + (NT / C) * 8 * CP * it, u)];
     fft::Dft<8, false>::run(v);
     if (c < rows) {
       const int k2 = tile * C + c;
@@ -218,18 +271,19 @@ __global__ void fine_argmax_kernel(const unsigned long long* partial, int ntiles
   }
 }
 
-__global__ void fine_tables_kernel(cpx* w2048, cpx* wlo) {
+__global__ void fine_tables_kernel(cpx* w2048, cpx* wlo, cpx* w128) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= R) return;
   double s, c;
   sincospi(-2.0 * (double)i / (double)R, &s, &c);
   w2048[i] = make_float2((float)c, (float)s);
+  if (i % (R / 128) == 0) w128[i / (R / 128)] = w2048[i];
   sincospi(-2.0 * (double)i / (double)NFFT, &s, &c);
   wlo[i] = make_float2((float)c, (float)s);
 }
 
 struct Scratch {
-  DevBuf w2048, wlo, y, partial, stripped;
+  DevBuf w2048, wlo, w128, y, partial, stripped;
   bool tables = false;
 };
 static Scratch g_fine;
@@ -240,8 +294,9 @@ int run(Args a, int n_items, int* d_index, cudaStream_t s) {
   if ((a.nvalid + R - 1) / R > 256) return fail(SGX_ERR_ARG, "fine search", "more than 256 non-zero rows");
   Scratch& g = g_fine;
   if (!g.tables) {
-    if (g.w2048.reserve(sizeof(cpx) * R) || g.wlo.reserve(sizeof(cpx) * R)) return fail(SGX_ERR_CUDA, "cudaMalloc", "fine tables");
-    SGX_COUNTED_LAUNCH(fine_tables_kernel, dim3(R / 256), dim3(256), 0, s, g.w2048.as<cpx>(), g.wlo.as<cpx>());
+    if (g.w2048.reserve(sizeof(cpx) * R) || g.wlo.reserve(sizeof(cpx) * R) || g.w128.reserve(sizeof(cpx) * 128))
+      return fail(SGX_ERR_CUDA, "cudaMalloc", "fine tables");
+    SGX_COUNTED_LAUNCH(fine_tables_kernel, dim3(R / 256), dim3(256), 0, s, g.w2048.as<cpx>(), g.wlo.as<cpx>(), g.w128.as<cpx>());
     g.tables = true;
   }
   const int col_tiles = R / (2 * C), row_tiles = (ROWS_KEPT + C - 1) / C;
@@ -256,11 +311,12 @@ int run(Args a, int n_items, int* d_index, cudaStream_t s) {
       g.partial.reserve(sizeof(unsigned long long) * (size_t)chunk * row_tiles))
     return fail(SGX_ERR_CUDA, "cudaMalloc", "fine search scratch");
   const size_t smem = sizeof(cpx) * (size_t)R * CP;            // step 2: tile only (twiddles through L1)
-  const size_t smem_cols = smem + sizeof(cpx) * R;              // step 1: tile + twiddle table
+  const size_t smem_cols = smem + sizeof(cpx) * (R + 128);      // step 1: tile + twiddle tables (2048 and 128 entries)
   SGX_CUDA(cudaFuncSetAttribute(fine_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
   SGX_CUDA(cudaFuncSetAttribute(fine_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   a.w2048 = g.w2048.as<cpx>();
   a.wlo = g.wlo.as<cpx>();
+  a.w128 = g.w128.as<cpx>();
   a.y = g.y.as<cpx>();
   a.partial = g.partial.as<unsigned long long>();
   const FineItem* items = a.items;

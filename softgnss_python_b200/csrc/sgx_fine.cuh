@@ -21,6 +21,7 @@ struct Args {
   int lo, hi;                    // candidate bins lo <= k < hi; the key index is k - lo (slice-relative, :186-187)
   const cpx* w2048;              // [2048] exp(-2 pi i q / 2048)
   const cpx* wlo;                // [2048] exp(-2 pi i q / 2^22)
+  const cpx* w128;               // [128] exp(-2 pi i q / 128)
   float* stripped;               // [items][strip_stride] (x - mean) * code, zero-padded to whole rows of 2048
   long long strip_stride;
   cpx* y;                        // [items][1025][2048] step-1 output
