@@ -133,23 +133,35 @@ __global__ void __launch_bounds__(NT, 2) fine_cols_kernel(Args a) {
   for (int i = tid; i < R; i += NT) W[i] = a.w2048[i];        // once per (persistent) CTA
   if (tid < 128) W128[tid] = a.w128[tid];
   const int n_rows = (a.nvalid + R - 1) / R;    // rows n2 that hold samples (187 of 2048: the rest is zero padding)
-  constexpr int COL_TILES = R / (2 * C);
+  constexpr int COL_TILES = R / (2 * C), PIT = 128 * C / NT;
+  static_assert(128 * C % NT == 0, "whole iterations");
+  // the two non-zero inputs of this thread's first-stage butterflies, fetched one work item ahead (they travel during
+  // the output walk of the previous tile).  Code-stripped samples of the detection (strip_kernel), padded with zeros to
+  // whole rows: two reals = one element
+  cpx p0[PIT], p1[PIT];
+  auto fetch = [&](int work) {
+    const int tile = work % COL_TILES, item = work / COL_TILES;
+    const cpx* xs = reinterpret_cast<const cpx*>(a.stripped + (long long)item * a.strip_stride) + tile * C;
+#pragma unroll
+    for (int it = 0; it < PIT; ++it) {
+      const int c = tid % C, j = tid / C + (NT / C) * it;
+      p0[it] = j < n_rows ? __ldg(xs + (long long)j * (R / 2) + c) : make_float2(0.f, 0.f);
+      p1[it] = j + 128 < n_rows ? __ldg(xs + (long long)(j + 128) * (R / 2) + c) : make_float2(0.f, 0.f);
+    }
+  };
+  if (blockIdx.x < COL_TILES * a.n_items) fetch(blockIdx.x);
 #pragma unroll 1
   for (int work = blockIdx.x; work < COL_TILES * a.n_items; work += gridDim.x) {
   const int tile = work % COL_TILES, item = work / COL_TILES;
-  // code-stripped samples of this detection (strip_kernel), padded with zeros to whole rows: two reals = one element
-  const cpx* xs = reinterpret_cast<const cpx*>(a.stripped + (long long)item * a.strip_stride) + tile * C;
   // Pruned first stage (radix 16 over rows j + 128 u): only u = 0 and u = 1 can be non-zero, so
   //   y[u'] = (v0 + w_16^u' v1) w_2048^(j u')
-  // straight from global memory into the tile (requires n_rows <= 256; it is 187).
+  // straight from the prefetched registers into the tile (requires n_rows <= 256; it is 187).
   __syncthreads();   // the twiddle table is complete
-  static_assert(128 * C % NT == 0, "whole iterations");
 #pragma unroll
-  for (int it = 0; it < 128 * C / NT; ++it) {
+  for (int it = 0; it < PIT; ++it) {
     const int c = tid % C, j = tid / C + (NT / C) * it;          // rows j + 128 u: j < 128 shares no bit with 128 u
     const int a0 = at(tid / C, c);
-    const cpx v0 = j < n_rows ? __ldg(xs + (long long)j * (R / 2) + c) : make_float2(0.f, 0.f);
-    const cpx v1 = j + 128 < n_rows ? __ldg(xs + (long long)(j + 128) * (R / 2) + c) : make_float2(0.f, 0.f);
+    const cpx v0 = p0[it], v1 = p1[it];
     x[at_off(a0, (NT / C) * it)] = fft::cadd(v0, v1);
 #pragma unroll
     for (int u = 1; u < 16; ++u)   // W[(128 + j) u] = w_16^u W[j u]: one table read per output
@@ -160,6 +172,7 @@ __global__ void __launch_bounds__(NT, 2) fine_cols_kernel(Args a) {
   __syncthreads();
   dif_stage<8, 8, false>(x, W, tid);
   __syncthreads();
+  if (work + (int)gridDim.x < COL_TILES * a.n_items) fetch(work + gridDim.x);
   // separate the two real columns of every complex column, apply w_N^(n1 k2), store Y[k2][n1].  Items are walked in
   // tile-position order (k2 = ka + 16 kb + 256 kc sits at row (16 ka + kb) 8 + kc): a half-warp reads 4 consecutive
   // rows x 4 columns, conflict-free; k2 = 1024 (position 4) is done by the first C threads.
@@ -178,9 +191,12 @@ __global__ void __launch_bounds__(NT, 2) fine_cols_kernel(Args a) {
     cpx ya = make_float2(zp.x + zm.x, zp.y - zm.y);           // 2 X_a[k2]
     cpx yb = make_float2(zp.y + zm.y, zm.x - zp.x);           // 2 X_b[k2]
     const int n1 = tile * 2 * C + 2 * c;
-    const int ma = n1 * k2, mb = ma + k2;                       // < 2^21: no wrap modulo N = 2^22
-    ya = fft::cmulf(ya, fft::cmulf(W[ma >> 11], __ldg(a.wlo + (ma & (R - 1)))));
-    yb = fft::cmulf(yb, fft::cmulf(W[mb >> 11], __ldg(a.wlo + (mb & (R - 1)))));
+    const int ma = n1 * k2;                                     // (n1 + 1) k2 < 2^21: no wrap modulo N = 2^22
+    // w_N^ma from the two-level table; w_N^mb = w_N^ma w_N^k2 with k2 < 2048 straight from the low table (one random
+    // shared-memory read and one random global read less per pair)
+    const cpx ta = fft::cmulf(W[ma >> 11], __ldg(a.wlo + (ma & (R - 1))));
+    ya = fft::cmulf(ya, ta);
+    yb = fft::cmulf(yb, fft::cmulf(ta, __ldg(a.wlo + k2)));
     *reinterpret_cast<float4*>(out + (long long)k2 * R + 2 * c) = make_float4(ya.x, ya.y, yb.x, yb.y);
   }
   __syncthreads();   // the tile is rewritten by the next work item
