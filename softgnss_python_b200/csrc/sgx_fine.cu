@@ -129,6 +129,7 @@ __global__ void __launch_bounds__(NT, 2) fine_cols_kernel(Args a) {
   cpx* x = reinterpret_cast<cpx*>(smem);
   cpx* W = x + R * CP;
   cpx* W128 = W + R;
+  float4* S = reinterpret_cast<float4*>(W128 + 128);   // [16][C] per-tile twiddle steps of the output walk
   const int tid = threadIdx.x;
   for (int i = tid; i < R; i += NT) W[i] = a.w2048[i];        // once per (persistent) CTA
   if (tid < 128) W128[tid] = a.w128[tid];
@@ -153,6 +154,13 @@ __global__ void __launch_bounds__(NT, 2) fine_cols_kernel(Args a) {
 #pragma unroll 1
   for (int work = blockIdx.x; work < COL_TILES * a.n_items; work += gridDim.x) {
   const int tile = work % COL_TILES, item = work / COL_TILES;
+  if (tid < 16 * C) {   // S[it][c] = (w_N^(n1 it), w_N^((n1 + 1) it)), n1 = first real column of complex column c (read after 3 barriers)
+    const int it = tid / C, n1 = tile * 2 * C + 2 * (tid % C);
+    const int m = n1 * it;                                    // < 2^15
+    const cpx sa = fft::cmulf(a.w2048[m >> 11], __ldg(a.wlo + (m & (R - 1))));
+    const cpx sb = fft::cmulf(sa, __ldg(a.wlo + it));
+    S[tid] = make_float4(sa.x, sa.y, sb.x, sb.y);
+  }
   // Pruned first stage (radix 16 over rows j + 128 u): only u = 0 and u = 1 can be non-zero, so
   //   y[u'] = (v0 + w_16^u' v1) w_2048^(j u')
   // straight from the prefetched registers into the tile (requires n_rows <= 256; it is 187).
@@ -173,27 +181,40 @@ __global__ void __launch_bounds__(NT, 2) fine_cols_kernel(Args a) {
   dif_stage<8, 8, false>(x, W, tid);
   __syncthreads();
   if (work + (int)gridDim.x < COL_TILES * a.n_items) fetch(work + gridDim.x);
-  // separate the two real columns of every complex column, apply w_N^(n1 k2), store Y[k2][n1].  Items are walked in
-  // tile-position order (k2 = ka + 16 kb + 256 kc sits at row (16 ka + kb) 8 + kc): a half-warp reads 4 consecutive
-  // rows x 4 columns, conflict-free; k2 = 1024 (position 4) is done by the first C threads.
+  // separate the two real columns of every complex column, apply w_N^(n1 k2), store Y[k2][n1].  Thread (c, kc, kb) walks
+  // k2 = it + 16 kb + 256 kc, it = 0..15: the value sits at tile row it*128 + kb*8 + kc, its mirror R - k2 at
+  // (16 - it)*128 + (15 - kb)*8 + 7 - kc (it >= 1) -- constant offsets from two per-thread addresses; a half-warp reads
+  // 4 consecutive rows x 4 columns, conflict-free.  The twiddle w_N^(n1 k2) = w_N^(n1 k2(it = 0)) * S[it][c]: one
+  // two-level table product per thread and tile instead of one per value (random gathers: up to 7 wavefronts each).
+  // k2 = 1024 (position 4) is done by the first C threads.
   cpx* out = a.y + ((long long)item * ROWS_KEPT) * R + tile * 2 * C;
-  for (int idx = tid; idx < (R / 2) * C + C; idx += NT) {
-    int c, k2;
-    if (idx < (R / 2) * C) {
-      c = idx & (C - 1);
-      const int kc = (idx >> 2) & 3, g = idx >> 4;
-      k2 = (g >> 4) + 16 * (g & 15) + 256 * kc;
-    } else {
-      c = idx - (R / 2) * C;
-      k2 = R / 2;
+  {
+    const int c = tid & (C - 1), kc = (tid >> 2) & 3, kb = tid >> 4;
+    const int k20 = 16 * kb + 256 * kc;
+    const int m0 = (tile * 2 * C + 2 * c) * k20;               // (n1 + 1) k2 < 2^21: no wrap modulo N = 2^22
+    const cpx ba = fft::cmulf(W[m0 >> 11], __ldg(a.wlo + (m0 & (R - 1))));
+    const cpx bb = fft::cmulf(ba, __ldg(a.wlo + k20));
+    const int ap = at(kb * 8 + kc, c), am = at((15 - kb) * 8 + 7 - kc, c);
+    const int a_first = at(digit_rev((R - k20) & (R - 1)), c);
+    cpx* o = out + (long long)k20 * R + 2 * c;
+#pragma unroll
+    for (int it = 0; it < 16; ++it) {
+      const cpx zp = x[at_off(ap, 128 * it)];
+      const cpx zm = it == 0 ? x[a_first] : x[at_off(am, (16 - it) * 128)];
+      const float4 s4 = S[it * C + c];
+      cpx ya = make_float2(zp.x + zm.x, zp.y - zm.y);           // 2 X_a[k2]
+      cpx yb = make_float2(zp.y + zm.y, zm.x - zp.x);           // 2 X_b[k2]
+      ya = fft::cmulf(ya, fft::cmulf(ba, make_float2(s4.x, s4.y)));
+      yb = fft::cmulf(yb, fft::cmulf(bb, make_float2(s4.z, s4.w)));
+      *reinterpret_cast<float4*>(o + (long long)it * R) = make_float4(ya.x, ya.y, yb.x, yb.y);
     }
-    const cpx zp = x[at(digit_rev(k2), c)], zm = x[at(digit_rev((R - k2) & (R - 1)), c)];
-    cpx ya = make_float2(zp.x + zm.x, zp.y - zm.y);           // 2 X_a[k2]
-    cpx yb = make_float2(zp.y + zm.y, zm.x - zp.x);           // 2 X_b[k2]
-    const int n1 = tile * 2 * C + 2 * c;
-    const int ma = n1 * k2;                                     // (n1 + 1) k2 < 2^21: no wrap modulo N = 2^22
-    // w_N^ma from the two-level table; w_N^mb = w_N^ma w_N^k2 with k2 < 2048 straight from the low table (one random
-    // shared-memory read and one random global read less per pair)
+  }
+  if (tid < C) {
+    const int c = tid, k2 = R / 2;
+    const cpx zp = x[at(digit_rev(k2), c)], zm = zp;             // R - k2 = k2
+    cpx ya = make_float2(zp.x + zm.x, zp.y - zm.y);
+    cpx yb = make_float2(zp.y + zm.y, zm.x - zp.x);
+    const int ma = (tile * 2 * C + 2 * c) * k2;
     const cpx ta = fft::cmulf(W[ma >> 11], __ldg(a.wlo + (ma & (R - 1))));
     ya = fft::cmulf(ya, ta);
     yb = fft::cmulf(yb, fft::cmulf(ta, __ldg(a.wlo + k2)));
@@ -327,7 +348,7 @@ int run(Args a, int n_items, int* d_index, cudaStream_t s) {
       g.partial.reserve(sizeof(unsigned long long) * (size_t)chunk * row_tiles))
     return fail(SGX_ERR_CUDA, "cudaMalloc", "fine search scratch");
   const size_t smem = sizeof(cpx) * (size_t)R * CP;            // step 2: tile only (twiddles through L1)
-  const size_t smem_cols = smem + sizeof(cpx) * (R + 128);      // step 1: tile + twiddle tables (2048 and 128 entries)
+  const size_t smem_cols = smem + sizeof(cpx) * (R + 128) + sizeof(float4) * 16 * C;  // step 1: tile + twiddle tables (2048, 128) + per-tile steps
   SGX_CUDA(cudaFuncSetAttribute(fine_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
   SGX_CUDA(cudaFuncSetAttribute(fine_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   a.w2048 = g.w2048.as<cpx>();
