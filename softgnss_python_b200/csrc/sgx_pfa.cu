@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pfa_search_kernel(SearchArgs
   cpx* scr = a.scratch + (size_t)blockIdx.x * NB * SROW;
   const int ja = lane & (CA - 1), ka = lane / CA;
   const bool act = ka < P2;
-  const size_t off0 = (size_t)(act ? ka : 0) * NB + ja;
+  const int off0 = (act ? ka : 0) * CA + ja;
 
   const cpx* src = nullptr;
   const cpx* cod = nullptr;
@@ -141,19 +141,19 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pfa_search_kernel(SearchArgs
     }
   };
   cpx v[P1];
-  // code slice `sa` -> Y (two 16-byte copies per row), spectrum slice -> registers
+  // code slice `sa` -> Y (the slice is one contiguous block in the slice-major storage order: 16 bytes per lane, fully
+  // coalesced), spectrum slice -> registers (a row group of P2 x CA values is 224 contiguous bytes)
   auto fetch = [&](int sa) {
-    // row (lane >> 1) + 16 it, half (lane & 1): constant offsets per iteration, one predicate for the ragged tail
-    const cpx* q = cod + sa * CA + (size_t)(lane >> 1) * NB + (lane & 1) * 2;
-    cpx* yd = Y + (lane >> 1) * CA + (lane & 1) * 2;
+    const cpx* q = cod + sa * (NA * CA) + lane * 2;
+    cpx* yd = Y + lane * 2;
 #pragma unroll
-    for (int it = 0; it < (2 * NA + 31) / 32; ++it)
-      if (it < (2 * NA) / 32 || lane + 32 * it < 2 * NA) cp_async16(yd + it * 16 * CA, q + (size_t)it * 16 * NB);
+    for (int it = 0; it < (NA * CA + 63) / 64; ++it)
+      if (it < (NA * CA) / 64 || lane * 2 + 64 * it < NA * CA) cp_async16(yd + it * 64, q + it * 64);
     cp_async_commit();
     if (act) {
-      const cpx* p = src + off0 + sa * CA;
+      const cpx* p = src + sa * (NA * CA) + off0;
 #pragma unroll
-      for (int k1 = 0; k1 < P1; ++k1) v[k1] = __ldg(p + (size_t)k1 * P2 * NB);
+      for (int k1 = 0; k1 < P1; ++k1) v[k1] = __ldg(p + k1 * (P2 * CA));
     }
   };
 

@@ -55,8 +55,14 @@ struct Shape {
   static_assert(2 * NA * CA >= NB * CB, "pass-B tile must fit");
   static constexpr size_t smem_per_warp = sizeof(cpx) * (size_t)WARP_TILE;
   static constexpr size_t scratch_per_cta = sizeof(cpx) * (size_t)NB * SROW;
+  // Storage order of the spectra and code spectra ("residue order", slice-major): element (kA, kB), kA = k1*P2 + k2,
+  // kB = k3*P4 + k4, lives in pass-A slice kB / CA at row kA, column kB % CA.  A slice (NA x CA values, 6 944 bytes) is
+  // one contiguous block: the search kernel copies a code slice with fully coalesced 16-byte cp.async (the
+  // [kA][NB] order took 16 shared-memory wavefronts per request instead of 4: every 32-byte row piece arrived on its
+  // own) and reads a spectrum row group (P2 x CA values) as 224 contiguous bytes instead of 7 separate sectors.
+  __host__ __device__ static constexpr int slot(int kA, int kB) { return ((kB / CA) * NA + kA) * CA + kB % CA; }
   static int storage_index(int k) {   // where frequency bin k of a natural-order spectrum is stored
-    return ((k % P1) * P2 + k % P2) * NB + (k % P3) * P4 + k % P4;
+    return slot((k % P1) * P2 + k % P2, (k % P3) * P4 + k % P4);
   }
 };
 
@@ -243,10 +249,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pfa_forward_kernel(ForwardAr
         for (int n3 = 0; n3 < P3; ++n3) u[n3] = rp[(n3 * P4) * CB];
         fft::Dft<P3, false>::run(u);
         if (valid) {
-          cpx* o = out + (size_t)kA * NB + k4;
 #pragma unroll
           for (int k3 = 0; k3 < P3; ++k3)
-            o[k3 * P4] = make_float2(u[k3].x * a.scale, a.conj ? -u[k3].y * a.scale : u[k3].y * a.scale);
+            out[S::slot(kA, k3 * P4 + k4)] = make_float2(u[k3].x * a.scale, a.conj ? -u[k3].y * a.scale : u[k3].y * a.scale);
         }
       }
       __syncwarp();
