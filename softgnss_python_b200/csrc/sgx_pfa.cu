@@ -101,7 +101,9 @@ __device__ __forceinline__ unsigned long long block_max(unsigned long long key, 
 // Per warp two shared-memory buffers of NA x 4 values: X (work tile) and Y (code-spectrum slice, filled by cp.async
 // one slice ahead); the spectrum slice of the next slice travels in registers while the current one goes through
 // its second stage and the scratch store.  Pass B uses X and Y together as one NB x 8 tile.
-template <int P1, int P2, int P3, int P4, int WARPS, int MINB, bool MASKED, bool UNROLL31 = false>
+// BULK: the code slice is fetched by one TMA 1-D bulk copy per slice (cp.async.bulk, completion on a per-warp mbarrier)
+// instead of 14 cp.async per lane.
+template <int P1, int P2, int P3, int P4, int WARPS, int MINB, bool MASKED, bool UNROLL31 = false, bool BULK = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB) pfa_search_kernel(SearchArgs a) {
   typedef Shape<P1, P2, P3, P4> S;
   static_assert(P1 == 31, "stage 1 is the grouped radix-31 butterfly");
@@ -111,7 +113,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pfa_search_kernel(SearchArgs
   static_assert(CA == 4 && P3 / KB == 4, "copy loops / register ping-pong");
   SGX_DYN_SMEM(smem);
   __shared__ unsigned long long red[2][WARPS];
+  __shared__ unsigned long long cbar[WARPS];
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  unsigned cphase = 0;
+  if (BULK) {
+    if (tid < WARPS) mbar_init(&cbar[tid], 1);
+    __syncthreads();
+  }
   cpx* X = reinterpret_cast<cpx*>(smem) + (size_t)w * S::WARP_TILE;
   cpx* Y = X + NA * CA;
   cpx* scr = a.scratch + (size_t)blockIdx.x * NB * SROW;
@@ -144,12 +152,16 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pfa_search_kernel(SearchArgs
   // code slice `sa` -> Y (the slice is one contiguous block in the slice-major storage order: 16 bytes per lane, fully
   // coalesced), spectrum slice -> registers (a row group of P2 x CA values is 224 contiguous bytes)
   auto fetch = [&](int sa) {
-    const cpx* q = cod + sa * (NA * CA) + lane * 2;
-    cpx* yd = Y + lane * 2;
+    if (BULK) {
+      if (lane == 0) bulk_load(Y, cod + sa * (NA * CA), (unsigned)(sizeof(cpx) * NA * CA), &cbar[w]);
+    } else {
+      const cpx* q = cod + sa * (NA * CA) + lane * 2;
+      cpx* yd = Y + lane * 2;
 #pragma unroll
-    for (int it = 0; it < (NA * CA + 63) / 64; ++it)
-      if (it < (NA * CA) / 64 || lane * 2 + 64 * it < NA * CA) cp_async16(yd + it * 64, q + it * 64);
-    cp_async_commit();
+      for (int it = 0; it < (NA * CA + 63) / 64; ++it)
+        if (it < (NA * CA) / 64 || lane * 2 + 64 * it < NA * CA) cp_async16(yd + it * 64, q + it * 64);
+      cp_async_commit();
+    }
     if (act) {
       const cpx* p = src + sa * (NA * CA) + off0;
 #pragma unroll
@@ -164,7 +176,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pfa_search_kernel(SearchArgs
     // ---------------- pass A: DFT over (k1, k2); slice = CA values of kB = k3*P4 + k4 --------------------------------
 #pragma unroll 1
     for (int sa = w; sa < S::NSA; sa += WARPS) {
-      cp_async_wait_all();
+      if (BULK) {
+        mbar_wait(&cbar[w], cphase);
+        cphase ^= 1;
+      } else {
+        cp_async_wait_all();
+      }
       __syncwarp();
       // stage 1 (radix 31): lane (k2 = ka, column ja); rows k1*P2 + k2 -> tau1*P2 + k2
       if (act) {
@@ -263,14 +280,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pfa_search_kernel(SearchArgs
   }
 }
 
-template <int WARPS, int MINB, bool MASKED, bool UNROLL31 = false>
+template <int WARPS, int MINB, bool MASKED, bool UNROLL31 = false, bool BULK = false>
 static int launch_cfg(SearchArgs args, DevBuf& scratch, cudaStream_t s) {
   typedef SearchShape S;
   int dev = 0, n_sm = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   if (n_sm <= 0) n_sm = 148;
-  auto kfn = pfa_search_kernel<31, 7, 16, 11, WARPS, MINB, MASKED, UNROLL31>;
+  auto kfn = pfa_search_kernel<31, 7, 16, 11, WARPS, MINB, MASKED, UNROLL31, BULK>;
   const size_t smem = S::smem_per_warp * WARPS;
   SGX_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
@@ -328,7 +345,7 @@ static int launch_cfg(SearchArgs args, DevBuf& scratch, cudaStream_t s) {
 
 template <bool MASKED>
 static int launch_search_t(SearchArgs args, DevBuf& scratch, cudaStream_t s) {
-  int cfg = 143;  // [1]WC: warps per CTA x CTAs per SM (measured on B200, 59 392 transforms: 4x3 13.7 ms, 6x2 14.6, 12x1 14.5; 143 = 4x3 with the radix-31 butterfly unrolled, 13.5 ms)
+  int cfg = 543;  // [1]WC: warps per CTA x CTAs per SM (measured on B200, 59 392 transforms: 4x3 13.7 ms, 6x2 14.6, 12x1 14.5; 143 = 4x3 with the radix-31 butterfly unrolled, 13.5 ms)
   if (const char* e = getenv("SGX_PFA_CFG")) cfg = atoi(e);
   switch (cfg) {
     case 72: return launch_cfg<7, 2, MASKED>(args, scratch, s);
@@ -340,7 +357,8 @@ static int launch_search_t(SearchArgs args, DevBuf& scratch, cudaStream_t s) {
     case 153: return launch_cfg<5, 3, MASKED, true>(args, scratch, s);    // 15 warps per SM, 136 registers
     case 144: return launch_cfg<4, 4, MASKED, true>(args, scratch, s);    // 16 warps per SM, 128 registers
     case 43: return launch_cfg<4, 3, MASKED>(args, scratch, s);           // rolled radix-31 groups (21.4 ms per batch)
-    default: return launch_cfg<4, 3, MASKED, true>(args, scratch, s);     // radix-31 butterfly fully unrolled (21.2 ms)
+    case 143: return launch_cfg<4, 3, MASKED, true>(args, scratch, s);    // radix-31 butterfly fully unrolled, code slices by cp.async (11.34 ms)
+    default: return launch_cfg<4, 3, MASKED, true, true>(args, scratch, s);   // + code slices by TMA bulk copy (11.23 ms)
   }
 }
 
