@@ -12,7 +12,7 @@ namespace pfa {
 template <class S, int WARPS, int MODE>
 __device__ __forceinline__ void pass_b(const cpx* scr, cpx* X, int w, int lane, int cp, int chip, float& best, int& bidx) {
   constexpr int P2 = S::p2, P3 = S::p3, P4 = S::p4;
-  constexpr int NA = S::NA, N = S::N, SROW = S::SROW, CB = S::CB, KB = 32 / CB;
+  constexpr int NA = S::NA, N = S::N, CB = S::CB, KB = 32 / CB;
   constexpr int Q1 = N / S::p1, Q2 = N / P2, Q3 = N / P3, Q4 = N / P4;
   const int jb = lane & (CB - 1), kb = lane / CB;
   // Two register sets in flight: within a slice the loads of round r+2 travel while round r is computed, and the first
@@ -20,11 +20,11 @@ __device__ __forceinline__ void pass_b(const cpx* scr, cpx* X, int w, int lane, 
   // many of these loads come from HBM).
   static_assert(P3 / KB == 4, "four rounds per slice");
   cpx ua[P4], ub[P4];
+  // round r of slice sb: k3 = kb + KB*r for the lanes' kb, all k4: the P4 pass-A slices r*P4 + k4, one 256-byte block each
   auto load_round = [&](cpx* u, int sb, int r) {
-    const int tA = sb * CB + jb;
-    const cpx* p = scr + (size_t)((kb + KB * r) * P4) * SROW + (tA < NA ? tA : 0);
+    const cpx* p = scr + ((sb * S::NSA + r * P4) * S::CA * CB) + lane;
 #pragma unroll
-    for (int k4 = 0; k4 < P4; ++k4) u[k4] = __ldcg(p + (size_t)k4 * SROW);
+    for (int k4 = 0; k4 < P4; ++k4) u[k4] = __ldcg(p + k4 * (S::CA * CB));
   };
   auto do_round = [&](cpx* u, int r) {
     fft::Dft<P4, true>::run(u);
@@ -232,22 +232,25 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pfa_search_kernel(SearchArgs
         for (int t2 = 0; t2 < P2; ++t2) rp[t2 * CA] = u[t2];
       }
       __syncwarp();
-      // tile row c = tauA holds the 4 columns of this slice; a lane pair takes a row (16 bytes each), column j goes to
-      // scratch row kB = sa*4 + j
+      // tile row c = tauA holds the 4 columns of this slice; a lane pair takes a row (16 bytes each); in the scratch
+      // (Shape::scratch_index) the 16 rows of a request are four 64-byte runs in two lines
       {
-        cpx* dst = scr + (size_t)(sa * CA + (lane & 1) * 2) * SROW;
+        const int half = (lane & 1) * 2, c0 = lane >> 1;
+        cpx* dst = scr + ((c0 >> 3) * S::NSA + sa) * (CA * CB) + half * CB + (c0 & 7);
+        constexpr int STEP16 = 2 * S::NSA * CA * CB;     // 16 rows further: two kA / CB groups
 #pragma unroll 1
-        for (int c = lane >> 1; c < NA; c += 32) {      // two rows per iteration: both loads before the four stores
-          const float4 x = *reinterpret_cast<const float4*>(X + c * CA + (lane & 1) * 2);
+        for (int c = c0; c < NA; c += 32) {      // two rows per iteration: both loads before the four stores
+          const float4 x = *reinterpret_cast<const float4*>(X + c * CA + half);
           const bool second = c + 16 < NA;
           float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (second) y = *reinterpret_cast<const float4*>(X + (c + 16) * CA + (lane & 1) * 2);
-          __stcg(dst + c, make_float2(x.x, x.y));
-          __stcg(dst + SROW + c, make_float2(x.z, x.w));
+          if (second) y = *reinterpret_cast<const float4*>(X + (c + 16) * CA + half);
+          __stcg(dst, make_float2(x.x, x.y));
+          __stcg(dst + CB, make_float2(x.z, x.w));
           if (second) {
-            __stcg(dst + c + 16, make_float2(y.x, y.y));
-            __stcg(dst + SROW + c + 16, make_float2(y.z, y.w));
+            __stcg(dst + STEP16, make_float2(y.x, y.y));
+            __stcg(dst + STEP16 + CB, make_float2(y.z, y.w));
           }
+          dst += 2 * STEP16;
         }
       }
       __syncwarp();

@@ -51,16 +51,26 @@ struct Shape {
   static constexpr int NSA = NB / CA, NSB = (NA + CB - 1) / CB;
   static_assert(NB % CA == 0, "pass-A slices must be whole");
   static_assert(P2 <= 32 / CA && P3 % (32 / CB) == 0, "lane mapping of the first stages");
+  static_assert(CA == 32 / CB && P3 % CA == 0, "a pass-A slice holds the k3 values of one pass-B round");
   static constexpr int WARP_TILE = 2 * NA * CA;   // complex values per warp: X + Y in pass A, one NB x CB tile in pass B
   static_assert(2 * NA * CA >= NB * CB, "pass-B tile must fit");
   static constexpr size_t smem_per_warp = sizeof(cpx) * (size_t)WARP_TILE;
   static constexpr size_t scratch_per_cta = sizeof(cpx) * (size_t)NB * SROW;
   // Storage order of the spectra and code spectra ("residue order", slice-major): element (kA, kB), kA = k1*P2 + k2,
-  // kB = k3*P4 + k4, lives in pass-A slice kB / CA at row kA, column kB % CA.  A slice (NA x CA values, 6 944 bytes) is
-  // one contiguous block: the search kernel copies a code slice with fully coalesced 16-byte cp.async (the
-  // [kA][NB] order took 16 shared-memory wavefronts per request instead of 4: every 32-byte row piece arrived on its
-  // own) and reads a spectrum row group (P2 x CA values) as 224 contiguous bytes instead of 7 separate sectors.
-  __host__ __device__ static constexpr int slot(int kA, int kB) { return ((kB / CA) * NA + kA) * CA + kB % CA; }
+  // kB = k3*P4 + k4, lives in pass-A slice (k3 / CA) * P4 + k4 at row kA, column k3 % CA.  A slice (NA x CA values,
+  // 6 944 bytes) is one contiguous block: the search kernel fetches a code slice with one bulk copy (the [kA][NB]
+  // order took 16 shared-memory wavefronts per cp.async request instead of 4: every 32-byte row piece arrived on its
+  // own) and reads a spectrum row group (P2 x CA values) as 224 contiguous bytes instead of 7 separate sectors.  The
+  // four columns of a slice are the k3 values one pass-B warp round reads together (k3 = kb + 4 r for its lanes
+  // kb = 0..3), so that the scratch can be laid out for 256-byte pass-B reads (see scratch_index).
+  __host__ __device__ static constexpr int slice_of(int kB) { return ((kB / P4) / CA) * P4 + kB % P4; }
+  __host__ __device__ static constexpr int slot(int kA, int kB) { return (slice_of(kB) * NA + kA) * CA + (kB / P4) % CA; }
+  // Scratch order of the intermediate (pass A -> pass B): [kA / CB][slice][column][kA % CB].  Pass A stores 16 tile rows
+  // as four 64-byte runs in two lines; a pass-B round (lane = column * CB + kA % CB, P4 slices of one k3 group) reads
+  // P4 consecutive 256-byte blocks.
+  __host__ __device__ static constexpr int scratch_index(int kA, int sa, int col) {
+    return (((kA / CB) * NSA + sa) * CA + col) * CB + kA % CB;
+  }
   static int storage_index(int k) {   // where frequency bin k of a natural-order spectrum is stored
     return slot((k % P1) * P2 + k % P2, (k % P3) * P4 + k % P4);
   }
