@@ -32,6 +32,9 @@ struct ProNco {  // A6: int8 sample x (sin + j cos) of bin k; batch = (rec*block
   const double* cps;  // [nbins] carrier cycles per sample = f_k / fs
   int nbins, blocks, n;
   double cps_bin;
+  static constexpr bool STAGED = true;   // prime-factor forward kernel: the block of n samples is gathered from shared memory
+  __device__ __forceinline__ const int8_t* block() const { return sig; }
+  __device__ __forceinline__ void use(const int8_t* staged) { sig = staged; }
   __device__ __forceinline__ void prepare(int batch) {
     const int bin = batch % nbins;
     const int rb = batch / nbins;
@@ -52,6 +55,7 @@ struct ProNco {  // A6: int8 sample x (sin + j cos) of bin k; batch = (rec*block
 struct ProCode {  // A5: row of the sampled C/A table (tiled over coherent ms), real input
   const int8_t* table;  // [32][n1]
   int n1;
+  static constexpr bool STAGED = false;
   __device__ __forceinline__ void prepare(int prn) { table += (long long)prn * n1; }
   __device__ __forceinline__ cpx load(int i) const { return make_float2((float)table[i % n1], 0.f); }
 };

@@ -174,23 +174,55 @@ struct ForwardArgs {
   int nbatch;
 };
 
+// Shared memory of the forward kernel: the staged input block (Pro::STAGED) and one tile per warp.
+template <class Pro, class S>
+struct ForwardSmem {
+  static constexpr int TILE = S::NA * S::CA > S::NB * S::CB ? S::NA * S::CA : S::NB * S::CB;   // complex values per warp
+  static constexpr int STAGE = Pro::STAGED ? (S::N + 127) / 128 * 128 : 0;                      // bytes
+  static constexpr size_t bytes(int warps) { return (size_t)STAGE + sizeof(cpx) * (size_t)TILE * warps; }
+};
+
+// Pro::STAGED: the prologue reads one int8 block of N samples per transform (ProNco).  The prime-factor input order
+// makes every lane of a load touch its own 32-byte sector, and every pass-A slice touches nearly all sectors of the
+// block: read from global memory that is 44 L2 reads of the block per transform.  The block is copied to shared memory
+// once per transform instead (the copy for the next transform is issued between pass A and pass B) and gathered there.
 template <class Pro, int P1, int P2, int P3, int P4, int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB) pfa_forward_kernel(ForwardArgs a, Pro pro0) {
   typedef Shape<P1, P2, P3, P4> S;
+  typedef ForwardSmem<Pro, S> M;
   static_assert(P1 == 31, "stage 1 is the radix-31 butterfly");
   constexpr int NA = S::NA, NB = S::NB, N = S::N, SROW = S::SROW;
   constexpr int Q1 = N / P1, Q2 = N / P2, Q3 = N / P3, Q4 = N / P4;
   constexpr int CA = S::CA, CB = S::CB, KA = 32 / CA, KB = 32 / CB;
   SGX_DYN_SMEM(smem);
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-  cpx* X = reinterpret_cast<cpx*>(smem) + (size_t)w * S::WARP_TILE;
+  int8_t* stage = reinterpret_cast<int8_t*>(smem);
+  cpx* X = reinterpret_cast<cpx*>(smem + M::STAGE) + (size_t)w * M::TILE;
   cpx* scr = a.scratch + (size_t)blockIdx.x * NB * SROW;
   const int ja = lane & (CA - 1), ka = lane / CA;
   const int jb = lane & (CB - 1), kb = lane / CB;
+  auto stage_in = [&](int item) {
+    if constexpr (Pro::STAGED) {
+      static_assert(N % 16 == 0, "16-byte copies");
+      Pro q = pro0;
+      q.prepare(item);
+      const int8_t* g = q.block();
+      if ((reinterpret_cast<unsigned long long>(g) & 15ull) == 0) {
+        for (int i = tid; i < N / 16; i += WARPS * 32) reinterpret_cast<uint4*>(stage)[i] = __ldg(reinterpret_cast<const uint4*>(g) + i);
+      } else {
+        for (int i = tid; i < N; i += WARPS * 32) stage[i] = g[i];
+      }
+    }
+  };
+  if (Pro::STAGED && blockIdx.x < a.nbatch) {
+    stage_in(blockIdx.x);
+    __syncthreads();
+  }
 #pragma unroll 1
   for (int item = blockIdx.x; item < a.nbatch; item += gridDim.x) {
     Pro pro = pro0;
     pro.prepare(item);
+    if constexpr (Pro::STAGED) pro.use(stage);
     // pass A: DFT over (n1, n2); slice = CA values of nB = n3*P4 + n4
 #pragma unroll 1
     for (int sa = w; sa < S::NSA; sa += WARPS) {
@@ -233,6 +265,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pfa_forward_kernel(ForwardAr
       __syncwarp();
     }
     __syncthreads();
+    if (Pro::STAGED && item + (int)gridDim.x < a.nbatch) stage_in(item + gridDim.x);   // every warp is done with the block
     // pass B: DFT over (n4, n3); slice = CB values of kA = k1*P2 + k2; output X[kA][k3*P4 + k4]
     cpx* out = a.out + (long long)item * a.out_stride;
 #pragma unroll 1
@@ -270,14 +303,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pfa_forward_kernel(ForwardAr
   }
 }
 
-// `batch` forward transforms of N = SearchShape::N points into out[batch][N] (residue order).  Grows `scratch`.
-template <class Pro>
-inline int launch_forward(Pro pro, int batch, cpx* out, float scale, int conj, DevBuf& scratch, cudaStream_t s) {
+template <class Pro, int WARPS, int MINB>
+inline int launch_forward_cfg(Pro pro, int batch, cpx* out, float scale, int conj, DevBuf& scratch, cudaStream_t s) {
   typedef Shape<31, 7, 16, 11> S;
-  if (batch <= 0) return SGX_OK;
-  constexpr int WARPS = 4, MINB = 4;
   auto kfn = pfa_forward_kernel<Pro, 31, 7, 16, 11, WARPS, MINB>;
-  const size_t smem = S::smem_per_warp * WARPS;
+  const size_t smem = ForwardSmem<Pro, S>::bytes(WARPS);
   SGX_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, n_sm = 0, occ = 0;
   cudaGetDevice(&dev);
@@ -292,6 +322,21 @@ inline int launch_forward(Pro pro, int batch, cpx* out, float scale, int conj, D
   SGX_COUNTED_LAUNCH(kfn, dim3((unsigned)grid), dim3(WARPS * 32), smem, s, a, pro);
   SGX_CUDA(cudaGetLastError());
   return SGX_OK;
+}
+
+// `batch` forward transforms of N = SearchShape::N points into out[batch][N] (residue order).  Grows `scratch`.
+template <class Pro>
+inline int launch_forward(Pro pro, int batch, cpx* out, float scale, int conj, DevBuf& scratch, cudaStream_t s) {
+  if (batch <= 0) return SGX_OK;
+  if constexpr (Pro::STAGED) {
+    // 38 KB of staged samples + 11 KB per warp: two CTAs per SM
+    static const int cfg = getenv("SGX_PFA_FWD_CFG") ? atoi(getenv("SGX_PFA_FWD_CFG")) : 62;
+    if (cfg == 42) return launch_forward_cfg<Pro, 4, 2>(pro, batch, out, scale, conj, scratch, s);
+    if (cfg == 81) return launch_forward_cfg<Pro, 8, 1>(pro, batch, out, scale, conj, scratch, s);
+    return launch_forward_cfg<Pro, 6, 2>(pro, batch, out, scale, conj, scratch, s);
+  } else {
+    return launch_forward_cfg<Pro, 4, 4>(pro, batch, out, scale, conj, scratch, s);
+  }
 }
 
 typedef Shape<31, 7, 16, 11> SearchShape;   // 38 192 = 31 * 7 * 16 * 11 (fs = 38.192 MHz, 1 ms)
