@@ -327,6 +327,12 @@ def run_gpu(args, rank, world):
         a1_ms = a0.elapsed_time(a1) / args.steps
         fp32_peak = L.fp32_peak(stream)                       # FFMA burn on this GPU, TFLOP/s
         acq_tflops = cells * FLOP_PER_CELL / (a_ms / 1e3) / 1e12
+        acq_traffic = None      # DRAM bytes of the search kernel per launch, from the committed ncu capture of this workload
+        try:
+            with open(os.path.join(ROOT, "profiles", "acq_traffic_r2.json")) as f:
+                acq_traffic = json.load(f).get("dram_bytes_per_launch") if areq == 32 else None
+        except (OSError, ValueError):
+            pass
         acq = {"metric": "acq search cells/s", "value": world * cells / (a_ms / 1e3), "unit": "cells/s",
                "ms_per_step": a_ms, "gpu_launches": int(alaunch),
                "config": {"workload": "config 1 settings (32 PRN x 29 bins x 38192 code phases + fine search), "
@@ -339,6 +345,7 @@ def run_gpu(args, rank, world):
                "roofline": {"bound": "fp32 (CUDA-core FFT; not HBM: 0.3 B/cell)",
                             "achieved": acq_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
                             "frac": acq_tflops / fp32_peak, "frac_of_nominal_74.5": acq_tflops / 74.5,
+                            "traffic": acq_traffic, "kernel": "sgx::pfa::pfa_search_kernel (68 % of the call)",
                             "note": "reference-formulation FLOPs (330/cell, SURVEY.md 8(d)); peak = FP32 FMA burn "
                                     "measured on this GPU in this run (sgx_fp32_peak; nominal 74.5)"}}
         if rank == 0 and not args.no_cpu:

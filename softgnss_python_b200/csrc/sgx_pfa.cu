@@ -364,23 +364,21 @@ static int launch_cfg(SearchArgs args, DevBuf& scratch, cudaStream_t s) {
 
 template <bool MASKED>
 static int launch_search_t(SearchArgs args, DevBuf& scratch, cudaStream_t s) {
-  int cfg = 543;  // [1]WC: warps per CTA x CTAs per SM (measured on B200, 59 392 transforms: 4x3 13.7 ms, 6x2 14.6, 12x1 14.5; 143 = 4x3 with the radix-31 butterfly unrolled, 13.5 ms)
+  // [v]WC: variant, warps per CTA x CTAs per SM.  Measured on B200 (59 392 transforms; the numbers of one column are
+  // from the same build): 4x3 divides the 44 + 28 slices of a transform evenly and wins every time --
+  //   first slice-major build: 4x3 11.30 ms, 6x2 11.59, 12x1 12.25, 8x2 16.19 (128 registers: the prefetch spills);
+  //   earlier: 7x2, 14x1, 16x1 slower still, 5x3 / 4x4 (136 / 128 registers) 25.7 ms.
+  int cfg = 543;
   if (const char* e = getenv("SGX_PFA_CFG")) cfg = atoi(e);
   switch (cfg) {
-    case 72: return launch_cfg<7, 2, MASKED>(args, scratch, s);
-    case 82: return launch_cfg<8, 2, MASKED>(args, scratch, s);
-    case 121: return launch_cfg<12, 1, MASKED>(args, scratch, s);
-    case 141: return launch_cfg<14, 1, MASKED>(args, scratch, s);
-    case 161: return launch_cfg<16, 1, MASKED>(args, scratch, s);
     case 62: return launch_cfg<6, 2, MASKED>(args, scratch, s);
-    case 153: return launch_cfg<5, 3, MASKED, true>(args, scratch, s);    // 15 warps per SM, 136 registers
-    case 144: return launch_cfg<4, 4, MASKED, true>(args, scratch, s);    // 16 warps per SM, 128 registers
-    case 43: return launch_cfg<4, 3, MASKED>(args, scratch, s);           // rolled radix-31 groups (21.4 ms per batch)
+    case 121: return launch_cfg<12, 1, MASKED>(args, scratch, s);
+    case 43: return launch_cfg<4, 3, MASKED>(args, scratch, s);           // rolled radix-31 groups, code slices by cp.async
     // + scratch lines discarded from L2 after pass B: DRAM traffic of the launch 35.2 -> 19.6 GB, L2 hit rate 45 -> 64 %,
     // long-scoreboard stalls 0.42 -> 0.26 per issue -- and 2 % slower (9.96 vs 9.73 ms): the kernel is not DRAM-bound
     case 643: return launch_cfg<4, 3, MASKED, true, true, true>(args, scratch, s);
-    case 143: return launch_cfg<4, 3, MASKED, true>(args, scratch, s);    // radix-31 butterfly fully unrolled, code slices by cp.async (11.34 ms)
-    default: return launch_cfg<4, 3, MASKED, true, true>(args, scratch, s);   // + code slices by TMA bulk copy (11.23 ms)
+    case 143: return launch_cfg<4, 3, MASKED, true>(args, scratch, s);    // radix-31 butterfly unrolled, code slices by cp.async
+    default: return launch_cfg<4, 3, MASKED, true, true>(args, scratch, s);   // + code slices by TMA bulk copy (-1 %)
   }
 }
 
