@@ -74,6 +74,24 @@ def test_prn_shards_and_batch_equal_single(recordings):
         assert np.array_equal(np.concatenate([p[f][0] for p in parts]), full1[f][0]), f
 
 
+def test_unaligned_device_signal_equals_aligned(recordings):
+    """The forward kernel stages the int8 block of a transform in shared memory with 16-byte copies when the block is
+    aligned and byte copies otherwise: a longSignal that starts at an odd device address (a view into a longer
+    recording, acquisition.py:49-52 slices the file at an arbitrary skip) must give the same results."""
+    import torch
+    from softgnss_python_b200.acquisition import acquire_batch
+    _, d1 = recordings["acq_c1"]
+    s = case_settings(CASES["acq_c1"])
+    n = 11 * N
+    ref = acquire_batch(torch.from_numpy(d1[:n].copy()).cuda().view(1, n), s)
+    for shift in (1, 3, 8):
+        buf = torch.zeros(n + 64, dtype=torch.int8, device="cuda")
+        buf[shift:shift + n] = torch.from_numpy(d1[:n].copy()).cuda()
+        got = acquire_batch(buf[shift:shift + n].view(1, n), s)
+        for f in ("carrFreq", "codePhase", "peakMetric"):
+            assert np.array_equal(got[f], ref[f]), (shift, f)
+
+
 def test_satellite_list_length_semantics(recordings):
     """acquisition.py:92 iterates range(len(acqSatelliteList)): a list of 5 searches PRN 1..5."""
     from softgnss_python_b200.acquisition import acquisition
