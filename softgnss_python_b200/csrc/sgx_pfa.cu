@@ -113,7 +113,7 @@ __device__ __forceinline__ unsigned long long block_max(unsigned long long key, 
 // Warp-independent slices: in pass A a warp owns 4 columns (kB values) x all NA rows, in pass B 8 columns (tauA
 // values) x all NB rows; every butterfly stage of a slice reads only what the same warp wrote, so the only
 // block-wide barriers are the two per transform (pass A -> pass B; key reduction / scratch reuse).
-// Per warp two shared-memory buffers of NA x 4 values: X (work tile) and Y (code-spectrum slice, filled by cp.async
+// Per warp two shared-memory buffers of NA x 4 values: X (work tile) and Y (code-spectrum slice, filled by a bulk copy
 // one slice ahead); the spectrum slice of the next slice travels in registers while the current one goes through
 // its second stage and the scratch store.  Pass B uses X and Y together as one NB x 8 tile.
 // BULK: the code slice is fetched by one TMA 1-D bulk copy per slice (cp.async.bulk, completion on a per-warp mbarrier)

@@ -13,14 +13,16 @@
 //   stages), and because both the spectra and the code spectra are produced by this library, they are simply stored in
 //   the residue order (StorePerm epilogue of the forward transforms); the output order only enters the arg-max key.
 //
-//   One CTA computes a whole transform: pass A (DFT over k1, k2; 11 tiles of 16 columns) writes its result to a
-//   CTA-private scratch row block in global memory, pass B (DFT over k3, k4; 14 tiles) reads it back.  The scratch of
-//   all resident CTAs (296 x 315 KB = 93 MB) is reused for every transform, so it lives in the 126 MB L2 and the
-//   36 GB/batch HBM round trip of the two-kernel version disappears; |.|^2 and the arg-max are taken from the
-//   registers of the last butterfly, and one key per transform is written.
+//   One CTA computes a whole transform: pass A (DFT over k1, k2) writes its result to a CTA-private scratch block in
+//   global memory, pass B (DFT over k3, k4) reads it back; |.|^2 and the maximum are taken from the registers of the
+//   last butterfly, and one key per transform is written.  The 36 GB/batch of separate-kernel intermediates become a
+//   scratch that is reused for every transform (444 resident CTAs x 315 KB).
 //
-//   A CTA is NG independent groups of 128 threads (named barriers), each working on its own tiles of the current
-//   transform; two __syncthreads per transform (pass A -> pass B, and the key reduction).
+//   Within a pass the work is split into warp-private slices (Shape: 4 columns x 217 rows in pass A, 8 columns x 176
+//   rows in pass B): every butterfly stage of a slice reads only what the same warp wrote, so the only block-wide
+//   barriers are the two per transform.  Spectra, code spectra and the scratch are stored in the order they are
+//   accessed (Shape::slot, Shape::scratch_index): a pass-A slice is one contiguous block (one TMA bulk copy for the code
+//   slice), a pass-B round reads consecutive 256-byte blocks.
 #pragma once
 #include "sgx_acq_types.cuh"
 #include "sgx_pfa_tables.h"
