@@ -19,7 +19,9 @@ __device__ __forceinline__ void l2_discard_line(const void* p) {
 //         masked kernel, which recomputes that row anyway);
 // MODE 1: exact arg-max, smallest index among equal values (numpy's rule);
 // MODE 2: maximum over the second-peak candidates of acquisition.py:147-159 around code phase cp.
-template <class S, int WARPS, int MODE, bool DISCARD>
+// DIRECT: the scratch columns are in the order the radix-P2 stage of pass A produces them, block tau2 * 4 + tau1 / 8,
+//         position tau1 % 8 (one padding column per 32), instead of tauA = tau1 * P2 + tau2.
+template <class S, int WARPS, int MODE, bool DISCARD, bool DIRECT>
 __device__ __forceinline__ void pass_b(const cpx* scr, cpx* X, int w, int lane, int cp, int chip, float& best, int& bidx) {
   constexpr int P2 = S::p2, P3 = S::p3, P4 = S::p4;
   constexpr int NA = S::NA, N = S::N, CB = S::CB, KB = 32 / CB;
@@ -46,7 +48,9 @@ __device__ __forceinline__ void pass_b(const cpx* scr, cpx* X, int w, int lane, 
 #pragma unroll 1
   for (int sb = w; sb < S::NSB; sb += WARPS) {
     const int tA = sb * CB + jb;
-    const bool valid = tA < NA;
+    static_assert(!DIRECT || (S::p1 == 31 && CB == 8 && S::NSB == 4 * P2), "block order of the direct store");
+    const int t1d = (sb & 3) * CB + jb, t2d = sb >> 2;
+    const bool valid = DIRECT ? t1d < S::p1 : tA < NA;
     // stage 1 (radix P4 over k4): lane (k3 = kb + KB*r, column jb); tile rows k3*P4 + k4 -> k3*P4 + tau4
     do_round(ua, 0);
     load_round(ua, sb, 2);
@@ -62,7 +66,7 @@ __device__ __forceinline__ void pass_b(const cpx* scr, cpx* X, int w, int lane, 
     }
     if (sb + WARPS < S::NSB) { load_round(ua, sb + WARPS, 0); load_round(ub, sb + WARPS, 1); }
     // stage 2 (radix P3 over k3): lane (tau4 = kb + KB*r, column jb); outputs stay in registers
-    const int baseA = valid ? ((tA / P2) * Q1 + (tA % P2) * Q2) % N : 0;
+    const int baseA = !valid ? 0 : DIRECT ? (t1d * Q1 + t2d * Q2) % N : ((tA / P2) * Q1 + (tA % P2) * Q2) % N;
 #pragma unroll 1
     for (int t4 = kb; t4 < P4; t4 += KB) {
       if (valid) {
@@ -119,7 +123,7 @@ __device__ __forceinline__ unsigned long long block_max(unsigned long long key, 
 // BULK: the code slice is fetched by one TMA 1-D bulk copy per slice (cp.async.bulk, completion on a per-warp mbarrier)
 // instead of 14 cp.async per lane.
 template <int P1, int P2, int P3, int P4, int WARPS, int MINB, bool MASKED, bool UNROLL31 = false, bool BULK = false,
-          bool DISCARD = false>
+          bool DISCARD = false, bool DIRECT = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB) pfa_search_kernel(SearchArgs a) {
   typedef Shape<P1, P2, P3, P4> S;
   static_assert(P1 == 31, "stage 1 is the grouped radix-31 butterfly");
@@ -237,6 +241,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pfa_search_kernel(SearchArgs
       // the next slice's operands travel while this slice goes through stage 2 and the scratch store
       if (sa + WARPS < S::NSA) fetch(sa + WARPS);
       // stage 2 (radix P2): lane (tau1 = ka + KA*r, column ja), in place
+      cpx* dblk = scr + sa * (CA * CB) + ja * CB + ka;     // DIRECT: block (tau2 * 4 + round), slice sa, column ja, position ka
 #pragma unroll 1
       for (int t1 = ka; t1 < P1; t1 += KA) {
         cpx u[P2];
@@ -244,13 +249,19 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pfa_search_kernel(SearchArgs
 #pragma unroll
         for (int k2 = 0; k2 < P2; ++k2) u[k2] = rp[k2 * CA];
         fft::Dft<P2, true>::run(u);
+        if (DIRECT) {   // one 256-byte block per store instruction: lanes (ka, ja) -> position ja * 8 + ka
 #pragma unroll
-        for (int t2 = 0; t2 < P2; ++t2) rp[t2 * CA] = u[t2];
+          for (int t2 = 0; t2 < P2; ++t2) __stcg(dblk + t2 * (4 * S::NSA * CA * CB), u[t2]);
+          dblk += S::NSA * CA * CB;
+        } else {
+#pragma unroll
+          for (int t2 = 0; t2 < P2; ++t2) rp[t2 * CA] = u[t2];
+        }
       }
       __syncwarp();
       // tile row c = tauA holds the 4 columns of this slice; a lane pair takes a row (16 bytes each); in the scratch
       // (Shape::scratch_index) the 16 rows of a request are four 64-byte runs in two lines
-      {
+      if (!DIRECT) {
         const int half = (lane & 1) * 2, c0 = lane >> 1;
         cpx* dst = scr + ((c0 >> 3) * S::NSA + sa) * (CA * CB) + half * CB + (c0 & 7);
         constexpr int STEP16 = 2 * S::NSA * CA * CB;     // 16 rows further: two kA / CB groups
@@ -276,19 +287,19 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pfa_search_kernel(SearchArgs
     if (!MASKED) {
       float best = 0.f;
       int unused = 0;
-      pass_b<S, WARPS, 0, DISCARD>(scr, X, w, lane, 0, 0, best, unused);
+      pass_b<S, WARPS, 0, DISCARD, DIRECT>(scr, X, w, lane, 0, 0, best, unused);
       // (the barrier inside: every warp is done reading the scratch before the next transform overwrites it)
       const unsigned long long k = block_max<WARPS>(fft::peak_key(best, 0u), red[0], w, lane);
       if (tid == 0) a.partial[out_index] = k;
     } else {
       float best = -1.f;
       int bidx = 0x7fffffff;
-      pass_b<S, WARPS, 1, false>(scr, X, w, lane, 0, 0, best, bidx);
+      pass_b<S, WARPS, 1, false, DIRECT>(scr, X, w, lane, 0, 0, best, bidx);
       const unsigned long long k1 = block_max<WARPS>(best >= 0.f ? fft::peak_key(best, (unsigned)bidx) : 0ull, red[0], w, lane);
       const int cp = (int)fft::key_index(k1);
       best = -1.f;
       bidx = 0x7fffffff;
-      pass_b<S, WARPS, 2, DISCARD>(scr, X, w, lane, cp, a.chip, best, bidx);
+      pass_b<S, WARPS, 2, DISCARD, DIRECT>(scr, X, w, lane, cp, a.chip, best, bidx);
       const unsigned long long k2 = block_max<WARPS>(best >= 0.f ? fft::peak_key(best, (unsigned)bidx) : 0ull, red[1], w, lane);
       if (tid == 0) {
         a.partial[out_index] = k2;
@@ -299,14 +310,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pfa_search_kernel(SearchArgs
   }
 }
 
-template <int WARPS, int MINB, bool MASKED, bool UNROLL31 = false, bool BULK = false, bool DISCARD = false>
+template <int WARPS, int MINB, bool MASKED, bool UNROLL31 = false, bool BULK = false, bool DISCARD = false, bool DIRECT = false>
 static int launch_cfg(SearchArgs args, DevBuf& scratch, cudaStream_t s) {
   typedef SearchShape S;
   int dev = 0, n_sm = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   if (n_sm <= 0) n_sm = 148;
-  auto kfn = pfa_search_kernel<31, 7, 16, 11, WARPS, MINB, MASKED, UNROLL31, BULK, DISCARD>;
+  auto kfn = pfa_search_kernel<31, 7, 16, 11, WARPS, MINB, MASKED, UNROLL31, BULK, DISCARD, DIRECT>;
   const size_t smem = S::smem_per_warp * WARPS;
   SGX_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
@@ -368,7 +379,7 @@ static int launch_search_t(SearchArgs args, DevBuf& scratch, cudaStream_t s) {
   // from the same build): 4x3 divides the 44 + 28 slices of a transform evenly and wins every time --
   //   first slice-major build: 4x3 11.30 ms, 6x2 11.59, 12x1 12.25, 8x2 16.19 (128 registers: the prefetch spills);
   //   earlier: 7x2, 14x1, 16x1 slower still, 5x3 / 4x4 (136 / 128 registers) 25.7 ms.
-  int cfg = 543;
+  int cfg = 743;
   if (const char* e = getenv("SGX_PFA_CFG")) cfg = atoi(e);
   switch (cfg) {
     case 62: return launch_cfg<6, 2, MASKED>(args, scratch, s);
@@ -378,7 +389,10 @@ static int launch_search_t(SearchArgs args, DevBuf& scratch, cudaStream_t s) {
     // long-scoreboard stalls 0.42 -> 0.26 per issue -- and 2 % slower (9.96 vs 9.73 ms): the kernel is not DRAM-bound
     case 643: return launch_cfg<4, 3, MASKED, true, true, true>(args, scratch, s);
     case 143: return launch_cfg<4, 3, MASKED, true>(args, scratch, s);    // radix-31 butterfly unrolled, code slices by cp.async
-    default: return launch_cfg<4, 3, MASKED, true, true>(args, scratch, s);   // + code slices by TMA bulk copy (-1 %)
+    case 543: return launch_cfg<4, 3, MASKED, true, true>(args, scratch, s);   // + code slices by TMA bulk copy (-1 %): 9.71 ms
+    // + radix-7 outputs stored straight into the scratch (blocks in (tau2, tau1 / 8) order: every store instruction is one
+    // 256-byte block), no tile write-back, no copy loop: 9.01 ms, 99.8 instructions per point, issue 69 %
+    default: return launch_cfg<4, 3, MASKED, true, true, false, true>(args, scratch, s);
   }
 }
 

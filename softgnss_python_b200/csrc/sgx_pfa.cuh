@@ -67,9 +67,11 @@ struct Shape {
   // kb = 0..3), so that the scratch can be laid out for 256-byte pass-B reads (see scratch_index).
   __host__ __device__ static constexpr int slice_of(int kB) { return ((kB / P4) / CA) * P4 + kB % P4; }
   __host__ __device__ static constexpr int slot(int kA, int kB) { return (slice_of(kB) * NA + kA) * CA + (kB / P4) % CA; }
-  // Scratch order of the intermediate (pass A -> pass B): [kA / CB][slice][column][kA % CB].  Pass A stores 16 tile rows
-  // as four 64-byte runs in two lines; a pass-B round (lane = column * CB + kA % CB, P4 slices of one k3 group) reads
-  // P4 consecutive 256-byte blocks.
+  // Scratch order of the intermediate (pass A -> pass B): [block of CB values of kA][slice][column][position].  A pass-B
+  // round (lane = column * CB + position, P4 slices of one k3 group) reads P4 consecutive 256-byte blocks.  The default
+  // search kernel (DIRECT) numbers the kA values as its radix-P2 stage produces them -- block tau2 * 4 + tau1 / 8,
+  // position tau1 % 8, one padding value per 32 -- so that every store instruction of that stage writes one whole block;
+  // the copy-loop variant and this helper use block kA / CB, position kA % CB.
   __host__ __device__ static constexpr int scratch_index(int kA, int sa, int col) {
     return (((kA / CB) * NSA + sa) * CA + col) * CB + kA % CB;
   }
