@@ -506,6 +506,7 @@ struct AcqPlan {
   int n = 0, n1 = 0, nfft = 0, nvalid = 0;
   fft::Plan fwd, inv, fine;
   bool pfa = false;     // search transforms through pfa_search_kernel (spectra stored in residue order)
+  int pfa_p2 = 0;       // second factor of the prime-factor shape (7: N = 38 192, 3: N = 16 368)
   DevBuf perm, scratch;
   DevBuf codeF, table, chips, fidx, cps, sig, spec, work0, work1, partial, partial2, sel, sums, metric, cph, fbin,
       fitems, fpartial, findex;
@@ -568,17 +569,20 @@ static int ensure_plan(const sgx_settings* st, const int8_t* ca_table, const int
   }
   SGX_CUDA(cudaMemcpyAsync(a.cps.p, cps.data(), sizeof(double) * st->numFrqBins, cudaMemcpyHostToDevice, s));
   SGX_CUDA(cudaStreamSynchronize(s));
-  a.pfa = pfa_enabled() && a.n == SearchShape::N;
+  a.pfa_p2 = pfa_enabled() ? pfa::pfa_shape_p2(a.n) : 0;
+  a.pfa = a.pfa_p2 != 0;
   if (a.pfa) {
     std::vector<int> perm(a.n);
-    for (int k = 0; k < a.n; ++k) perm[k] = SearchShape::storage_index(k);
+    for (int k = 0; k < a.n; ++k) perm[k] = a.pfa_p2 == 7 ? SearchShape::storage_index(k) : pfa::SearchShape3::storage_index(k);
     if (a.perm.reserve(sizeof(int) * a.n)) return fail(SGX_ERR_CUDA, "cudaMalloc", "acquisition plan");
     SGX_CUDA(cudaMemcpyAsync(a.perm.p, perm.data(), sizeof(int) * a.n, cudaMemcpyHostToDevice, s));
     SGX_CUDA(cudaStreamSynchronize(s));
   }
   // A5: conj(FFT(code)) / n for all 32 PRNs
   if (a.pfa && pfa_forward_enabled())
-    rc = pfa::launch_forward(ProCode{a.table.as<int8_t>(), n1}, 32, a.codeF.as<cpx>(), 1.0f / (float)a.n, 1, a.scratch, s);
+    rc = a.pfa_p2 == 7
+             ? pfa::launch_forward<ProCode, 7>(ProCode{a.table.as<int8_t>(), n1}, 32, a.codeF.as<cpx>(), 1.0f / (float)a.n, 1, a.scratch, s)
+             : pfa::launch_forward<ProCode, 3>(ProCode{a.table.as<int8_t>(), n1}, 32, a.codeF.as<cpx>(), 1.0f / (float)a.n, 1, a.scratch, s);
   else if (a.pfa)
     rc = run_fft(a.fwd, false, 32, ProCode{a.table.as<int8_t>(), n1},
                  pfa::StorePerm{a.codeF.as<cpx>(), (long long)a.n, 1.0f / (float)a.n, 1, a.perm.as<int>(), nullptr},
@@ -702,9 +706,11 @@ extern "C" int sgx_acquire(const int8_t* sig, int64_t rec_stride, int64_t n_samp
   // ---- A6 + forward half of A7: one spectrum per (rec, block, bin) -----------------------------
   if (nspec > 32768 || npr > 32768)
     return fail(SGX_ERR_ARG, "sgx_acquire", "too many recordings in one call (split the batch)");
-  if (a.pfa && pfa_forward_enabled())
-    rc = pfa::launch_forward(ProNco{d_sig, stride, a.cps.as<double>(), nbins, blocks, (int)n, 0.0}, nspec, a.spec.as<cpx>(),
-                             1.f, 0, a.scratch, s);
+  if (a.pfa && pfa_forward_enabled()) {
+    const ProNco pn{d_sig, stride, a.cps.as<double>(), nbins, blocks, (int)n, 0.0};
+    rc = a.pfa_p2 == 7 ? pfa::launch_forward<ProNco, 7>(pn, nspec, a.spec.as<cpx>(), 1.f, 0, a.scratch, s)
+                       : pfa::launch_forward<ProNco, 3>(pn, nspec, a.spec.as<cpx>(), 1.f, 0, a.scratch, s);
+  }
   else if (a.pfa)
     rc = run_fft(a.fwd, false, nspec, ProNco{d_sig, stride, a.cps.as<double>(), nbins, blocks, (int)n, 0.0},
                  pfa::StorePerm{a.spec.as<cpx>(), n, 1.f, 0, a.perm.as<int>(), nullptr}, a.work0.as<cpx>(), a.work1.as<cpx>(), s);
@@ -719,7 +725,7 @@ extern "C" int sgx_acquire(const int8_t* sig, int64_t rec_stride, int64_t n_samp
     pfa::SearchArgs sa;
     sa.spec = a.spec.as<cpx>(); sa.codeF = a.codeF.as<cpx>(); sa.scratch = nullptr;
     sa.partial = a.partial.as<unsigned long long>(); sa.sel = nullptr; sa.sel_out = nullptr; sa.d = d; sa.nitems = nitems;
-    sa.chip = st->samplesPerCodeChip;
+    sa.chip = st->samplesPerCodeChip; sa.p2 = a.pfa_p2;
     rc = pfa::launch_search(sa, false, a.scratch, s);
     if (rc) return rc;
   } else
@@ -743,7 +749,7 @@ extern "C" int sgx_acquire(const int8_t* sig, int64_t rec_stride, int64_t n_samp
     pfa::SearchArgs sa;
     sa.spec = a.spec.as<cpx>(); sa.codeF = a.codeF.as<cpx>(); sa.scratch = nullptr;
     sa.partial = a.partial2.as<unsigned long long>(); sa.sel = a.sel.as<PeakSel>(); sa.sel_out = a.sel.as<PeakSel>(); sa.d = d; sa.nitems = npr;
-    sa.chip = st->samplesPerCodeChip;
+    sa.chip = st->samplesPerCodeChip; sa.p2 = a.pfa_p2;
     rc = pfa::launch_search(sa, true, a.scratch, s);
     if (rc) return rc;
   } else {

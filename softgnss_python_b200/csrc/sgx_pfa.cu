@@ -310,14 +310,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pfa_search_kernel(SearchArgs
   }
 }
 
-template <int WARPS, int MINB, bool MASKED, bool UNROLL31 = false, bool BULK = false, bool DISCARD = false, bool DIRECT = false>
+template <int WARPS, int MINB, bool MASKED, bool UNROLL31 = false, bool BULK = false, bool DISCARD = false, bool DIRECT = false,
+          int P2 = 7>
 static int launch_cfg(SearchArgs args, DevBuf& scratch, cudaStream_t s) {
-  typedef SearchShape S;
+  typedef Shape<31, P2, 16, 11> S;
   int dev = 0, n_sm = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   if (n_sm <= 0) n_sm = 148;
-  auto kfn = pfa_search_kernel<31, 7, 16, 11, WARPS, MINB, MASKED, UNROLL31, BULK, DISCARD, DIRECT>;
+  auto kfn = pfa_search_kernel<31, P2, 16, 11, WARPS, MINB, MASKED, UNROLL31, BULK, DISCARD, DIRECT>;
   const size_t smem = S::smem_per_warp * WARPS;
   SGX_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
@@ -379,6 +380,7 @@ static int launch_search_t(SearchArgs args, DevBuf& scratch, cudaStream_t s) {
   // from the same build): 4x3 divides the 44 + 28 slices of a transform evenly and wins every time --
   //   first slice-major build: 4x3 11.30 ms, 6x2 11.59, 12x1 12.25, 8x2 16.19 (128 registers: the prefetch spills);
   //   earlier: 7x2, 14x1, 16x1 slower still, 5x3 / 4x4 (136 / 128 registers) 25.7 ms.
+  if (args.p2 == 3) return launch_cfg<4, 3, MASKED, true, true, false, true, 3>(args, scratch, s);   // N = 16 368: the default build only
   int cfg = 743;
   if (const char* e = getenv("SGX_PFA_CFG")) cfg = atoi(e);
   switch (cfg) {

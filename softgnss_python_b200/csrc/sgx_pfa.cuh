@@ -42,6 +42,7 @@ struct SearchArgs {
   SearchDims d;
   long long nitems;
   int chip;                      // samples per chip (second-peak exclusion, acquisition.py:145)
+  int p2;                        // second factor of the transform length: 7 (N = 38 192) or 3 (N = 16 368)
 };
 
 template <int P1, int P2, int P3, int P4>
@@ -54,8 +55,8 @@ struct Shape {
   static_assert(NB % CA == 0, "pass-A slices must be whole");
   static_assert(P2 <= 32 / CA && P3 % (32 / CB) == 0, "lane mapping of the first stages");
   static_assert(CA == 32 / CB && P3 % CA == 0, "a pass-A slice holds the k3 values of one pass-B round");
-  static constexpr int WARP_TILE = 2 * NA * CA;   // complex values per warp: X + Y in pass A, one NB x CB tile in pass B
-  static_assert(2 * NA * CA >= NB * CB, "pass-B tile must fit");
+  // complex values per warp: X + Y in pass A, one NB x CB tile in pass B
+  static constexpr int WARP_TILE = 2 * NA * CA > NB * CB ? 2 * NA * CA : NB * CB;
   static constexpr size_t smem_per_warp = sizeof(cpx) * (size_t)WARP_TILE;
   static constexpr size_t scratch_per_cta = sizeof(cpx) * (size_t)NB * SROW;
   // Storage order of the spectra and code spectra ("residue order", slice-major): element (kA, kB), kA = k1*P2 + k2,
@@ -307,10 +308,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) pfa_forward_kernel(ForwardAr
   }
 }
 
-template <class Pro, int WARPS, int MINB>
+template <class Pro, int P2, int WARPS, int MINB>
 inline int launch_forward_cfg(Pro pro, int batch, cpx* out, float scale, int conj, DevBuf& scratch, cudaStream_t s) {
-  typedef Shape<31, 7, 16, 11> S;
-  auto kfn = pfa_forward_kernel<Pro, 31, 7, 16, 11, WARPS, MINB>;
+  typedef Shape<31, P2, 16, 11> S;
+  auto kfn = pfa_forward_kernel<Pro, 31, P2, 16, 11, WARPS, MINB>;
   const size_t smem = ForwardSmem<Pro, S>::bytes(WARPS);
   SGX_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, n_sm = 0, occ = 0;
@@ -328,22 +329,28 @@ inline int launch_forward_cfg(Pro pro, int batch, cpx* out, float scale, int con
   return SGX_OK;
 }
 
-// `batch` forward transforms of N = SearchShape::N points into out[batch][N] (residue order).  Grows `scratch`.
-template <class Pro>
+// `batch` forward transforms of N = 31 * P2 * 16 * 11 points into out[batch][N] (residue order).  Grows `scratch`.
+template <class Pro, int P2 = 7>
 inline int launch_forward(Pro pro, int batch, cpx* out, float scale, int conj, DevBuf& scratch, cudaStream_t s) {
   if (batch <= 0) return SGX_OK;
   if constexpr (Pro::STAGED) {
     // 38 KB of staged samples + 11 KB per warp: two CTAs per SM
     static const int cfg = getenv("SGX_PFA_FWD_CFG") ? atoi(getenv("SGX_PFA_FWD_CFG")) : 62;
-    if (cfg == 42) return launch_forward_cfg<Pro, 4, 2>(pro, batch, out, scale, conj, scratch, s);
-    if (cfg == 81) return launch_forward_cfg<Pro, 8, 1>(pro, batch, out, scale, conj, scratch, s);
-    return launch_forward_cfg<Pro, 6, 2>(pro, batch, out, scale, conj, scratch, s);
+    if constexpr (P2 == 7) {
+      if (cfg == 42) return launch_forward_cfg<Pro, P2, 4, 2>(pro, batch, out, scale, conj, scratch, s);
+      if (cfg == 81) return launch_forward_cfg<Pro, P2, 8, 1>(pro, batch, out, scale, conj, scratch, s);
+    }
+    return launch_forward_cfg<Pro, P2, 6, 2>(pro, batch, out, scale, conj, scratch, s);
   } else {
-    return launch_forward_cfg<Pro, 4, 4>(pro, batch, out, scale, conj, scratch, s);
+    return launch_forward_cfg<Pro, P2, 4, 4>(pro, batch, out, scale, conj, scratch, s);
   }
 }
 
 typedef Shape<31, 7, 16, 11> SearchShape;   // 38 192 = 31 * 7 * 16 * 11 (fs = 38.192 MHz, 1 ms)
+typedef Shape<31, 3, 16, 11> SearchShape3;  // 16 368 = 31 * 3 * 16 * 11 (fs = 16.3676 MHz rounded, 1 ms): the radix-31 stage
+                                            // runs on 12 of 32 lanes there, still ahead of the generic passes
+// second factor of the prime-factor shape for transform length n, 0 if there is none
+inline int pfa_shape_p2(long long n) { return n == SearchShape::N ? 7 : n == SearchShape3::N ? 3 : 0; }
 
 // All search transforms of a call (masked: the one second-peak transform per (rec, prn)) in one launch of resident
 // CTAs.  `scratch` is grown to gridDim.x x Shape::scratch_per_cta.  Defined in sgx_pfa.cu.

@@ -6,8 +6,9 @@ integration length (1, 2, 5, 10 ms) on one GPU.  Writes one JSON document (defau
 Every point: `recordings` synthetic recordings (8 satellites at 45 dB-Hz) generated on the device, reference settings
 otherwise (2 blocks with pick-max, 29 Doppler bins of 500 Hz, 32 PRNs, fine search on 10 ms); cells = recordings x 32 x
 29 x samplesPerCode (one code period of code phases is searched whatever the coherent length).  Timing: CUDA events,
-3 warm-up + 5 timed batches.  `engine` says which transform path ran: the prime-factor kernel exists only for
-N = 38 192 at 1 ms; every other length goes through the generic mixed-radix engine (run-time radices)."""
+3 warm-up + 5 timed batches.  `engine` says which transform path ran: the prime-factor kernel exists for
+N = 38 192 (31x7x16x11) and N = 16 368 (31x3x16x11) at 1 ms; every other length goes through the generic mixed-radix
+engine (run-time radices)."""
 import json
 import os
 import sys
@@ -67,7 +68,8 @@ def main():
                 pt = dict(fs_mhz=fs / 1e6, samples_per_code=n1, coherent_ms=coh, transform_length=n1 * coh,
                           factors=factor(n1 * coh), recordings=recs, ms_per_batch=ms, cells_per_s=cells / (ms / 1e3),
                           detected=int((res["carrFreq"] > 0).sum()), present=8 * recs,
-                          engine="prime-factor kernel (31x7x16x11)" if (n1 * coh == 38192) else "generic mixed-radix passes")
+                          engine="prime-factor kernel (31x7x16x11)" if (n1 * coh == 38192) else
+                          "prime-factor kernel (31x3x16x11)" if (n1 * coh == 16368) else "generic mixed-radix passes")
             except _native.NativeError as e:
                 pt = dict(fs_mhz=fs / 1e6, samples_per_code=n1, coherent_ms=coh, error=str(e))
             points.append(pt)
